@@ -1,0 +1,544 @@
+// C ABI of libanemoi_b200.so (declared in include/anemoi_b200.h): argument checking that mirrors the
+// reference's assert!s, device-buffer management for the host-pointer calls, and the level loop of the
+// Jive Merkle builder. All arithmetic happens in the per-field CUDA kernels (field_*.cu); there is no
+// CPU implementation of any hash function in this library.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "anemoi_b200.h"
+#include "kernel_args.h"
+#include "launch.h"
+
+namespace {
+
+using anemoi::KernelArgs;
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorMemoryAllocation) return ANEMOI_B200_ERR_NOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return ANEMOI_B200_ERR_NO_DEVICE;
+    return ANEMOI_B200_ERR_CUDA;
+}
+#define CK(call)                                           \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+typedef cudaError_t (*launch_fn)(int, const KernelArgs*, cudaStream_t);
+const launch_fn kLaunch[ANEMOI_NUM_FIELDS] = {
+    anemoi_launch_bls12_377, anemoi_launch_bls12_381, anemoi_launch_bn_254, anemoi_launch_ed_on_bls12_377,
+    anemoi_launch_jubjub,    anemoi_launch_pallas,    anemoi_launch_vesta,
+};
+const char* const kFieldName[ANEMOI_NUM_FIELDS] = {"bls12_377", "bls12_381", "bn_254", "ed_on_bls12_377",
+                                                   "jubjub",    "pallas",    "vesta"};
+const int kFieldLimbs[ANEMOI_NUM_FIELDS] = {6, 6, 4, 4, 4, 4, 4};
+// NUM_HASH_ROUNDS: src/<field>/anemoi_2_1/mod.rs:31-32, anemoi_4_3/mod.rs:31-32
+const int kRounds[ANEMOI_NUM_FIELDS][2] = {{21, 14}, {21, 14}, {21, 14}, {19, 13}, {21, 14}, {21, 14}, {21, 14}};
+
+int check_fi(int field, int inst) {
+    if (field < 0 || field >= ANEMOI_NUM_FIELDS) return ANEMOI_B200_ERR_FIELD;
+    if (inst != ANEMOI_INST_2_1 && inst != ANEMOI_INST_4_3) return ANEMOI_B200_ERR_INST;
+    return ANEMOI_B200_OK;
+}
+
+inline int width_of(int inst) { return inst == ANEMOI_INST_2_1 ? 2 : 4; }
+inline size_t felt_bytes(int field) { return (size_t)kFieldLimbs[field] * 8; }
+inline int aligned16(const void* a, const void* b) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
+int launch(int field, int inst, int mode, const void* in, void* out, const uint64_t* offsets, size_t n, size_t len,
+           cudaStream_t stream) {
+    KernelArgs a;
+    a.in = static_cast<const uint32_t*>(in);
+    a.out = static_cast<uint32_t*>(out);
+    a.offsets = reinterpret_cast<const unsigned long long*>(offsets);
+    a.n = n;
+    a.len = len;
+    a.mode = mode;
+    // felts are 32 or 48 bytes, so a 16-byte-aligned base keeps every felt 16-byte aligned
+    a.vec16 = aligned16(in, out);
+    if (mode == anemoi::MODE_HASH_BYTES) a.vec16 = aligned16(out, out);  // the byte input is read bytewise
+    const int cols = (mode == anemoi::MODE_TO_BYTES) ? 1 : (inst == ANEMOI_INST_2_1 ? 1 : 2);
+    cudaError_t e = kLaunch[field](cols, &a, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return ANEMOI_B200_OK;
+}
+
+int jive_mode(int inst, int k, int* out_per_state) {
+    if (inst == ANEMOI_INST_2_1) {
+        if (k != 2) return ANEMOI_B200_ERR_ARITY;  // assert!(k == 2)  anemoi_2_1/hasher.rs:107
+        *out_per_state = 1;
+        return anemoi::MODE_COMPRESS;
+    }
+    // assert!(STATE_WIDTH % k == 0); assert!(k % 2 == 0)  anemoi_4_3/hasher.rs:163-165
+    if (k == 2) {
+        *out_per_state = 2;
+        return anemoi::MODE_COMPRESS;
+    }
+    if (k == 4) {
+        *out_per_state = 1;
+        return anemoi::MODE_COMPRESS4;
+    }
+    return ANEMOI_B200_ERR_ARITY;
+}
+
+// RAII device buffer / device selection for the host-pointer entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+};
+
+struct DeviceScope {
+    int prev = -1;
+    int rc = ANEMOI_B200_OK;
+    explicit DeviceScope(int device) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "no CUDA device: %s", cudaGetErrorString(e));
+            rc = ANEMOI_B200_ERR_NO_DEVICE;
+            return;
+        }
+        if (device < 0 || device >= count) {
+            rc = ANEMOI_B200_ERR_ARG;
+            return;
+        }
+        cudaGetDevice(&prev);
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaSetDevice");
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Generic host wrapper: copy `in_bytes` up, run `body(d_in, d_out, stream)`, copy `out_bytes` back.
+template <class Body>
+int host_call(int device, const void* in, size_t in_bytes, void* out, size_t out_bytes, bool in_place, Body body) {
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    DevBuf d_in, d_out;
+    CK(d_in.alloc(in_bytes));
+    if (!in_place) CK(d_out.alloc(out_bytes));
+    cudaStream_t stream;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc = ANEMOI_B200_OK;
+    cudaError_t e = cudaMemcpyAsync(d_in.p, in, in_bytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "H2D copy");
+    if (rc == ANEMOI_B200_OK) rc = body(d_in.p, in_place ? d_in.p : d_out.p, stream);
+    if (rc == ANEMOI_B200_OK) {
+        e = cudaMemcpyAsync(out, in_place ? d_in.p : d_out.p, out_bytes, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+    }
+    e = cudaStreamSynchronize(stream);
+    if (rc == ANEMOI_B200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+int merkle_check(int field, int inst, int arity) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (!((inst == ANEMOI_INST_2_1 && arity == 2) || (inst == ANEMOI_INST_4_3 && arity == 4))) return ANEMOI_B200_ERR_ARITY;
+    return ANEMOI_B200_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int anemoi_b200_version(void) { return ANEMOI_B200_VERSION; }
+
+const char* anemoi_b200_strerror(int code) {
+    switch (code) {
+        case ANEMOI_B200_OK: return "ok";
+        case ANEMOI_B200_ERR_ARG: return "bad argument (null pointer, device index or variant)";
+        case ANEMOI_B200_ERR_FIELD: return "unknown field id";
+        case ANEMOI_B200_ERR_INST: return "unknown instantiation id";
+        case ANEMOI_B200_ERR_ARITY: return "compression factor / arity not supported by this instantiation";
+        case ANEMOI_B200_ERR_LENGTH: return "length is not a whole number of states or not a power of the arity";
+        case ANEMOI_B200_ERR_CUDA: return "CUDA runtime error (see anemoi_b200_last_cuda_error)";
+        case ANEMOI_B200_ERR_NO_DEVICE: return "no CUDA device available (this library has no CPU fallback)";
+        case ANEMOI_B200_ERR_NOMEM: return "device memory allocation failed";
+    }
+    return "unknown error code";
+}
+
+const char* anemoi_b200_last_cuda_error(void) { return g_cuda_err; }
+
+int anemoi_b200_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+int anemoi_b200_field_limbs(int field) {
+    if (field < 0 || field >= ANEMOI_NUM_FIELDS) return ANEMOI_B200_ERR_FIELD;
+    return kFieldLimbs[field];
+}
+int anemoi_b200_state_width(int inst) {
+    if (inst != ANEMOI_INST_2_1 && inst != ANEMOI_INST_4_3) return ANEMOI_B200_ERR_INST;
+    return width_of(inst);
+}
+int anemoi_b200_rate_width(int inst) {
+    if (inst != ANEMOI_INST_2_1 && inst != ANEMOI_INST_4_3) return ANEMOI_B200_ERR_INST;
+    return inst == ANEMOI_INST_2_1 ? 1 : 3;
+}
+int anemoi_b200_num_rounds(int field, int inst) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    return kRounds[field][inst];
+}
+const char* anemoi_b200_field_name(int field) {
+    if (field < 0 || field >= ANEMOI_NUM_FIELDS) return nullptr;
+    return kFieldName[field];
+}
+
+// ---- device-pointer entry points ---------------------------------------------------------------
+
+int anemoi_b200_permute_dev(int field, int inst, uint64_t* d_states, size_t n, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!d_states) return ANEMOI_B200_ERR_ARG;
+    return launch(field, inst, anemoi::MODE_PERMUTE, d_states, d_states, nullptr, n, 0, (cudaStream_t)stream);
+}
+
+int anemoi_b200_sbox_layer_dev(int field, int inst, uint64_t* d_states, size_t n, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!d_states) return ANEMOI_B200_ERR_ARG;
+    return launch(field, inst, anemoi::MODE_SBOX, d_states, d_states, nullptr, n, 0, (cudaStream_t)stream);
+}
+
+int anemoi_b200_compress_dev(int field, int inst, int k, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    int per = 0;
+    int mode = jive_mode(inst, k, &per);
+    if (mode < 0) return mode;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!d_in || !d_out) return ANEMOI_B200_ERR_ARG;
+    return launch(field, inst, mode, d_in, d_out, nullptr, n, 0, (cudaStream_t)stream);
+}
+
+int anemoi_b200_hash_field_dev(int field, int inst, const uint64_t* d_elems, size_t n_msgs, size_t felts_per_msg,
+                               uint64_t* d_digests, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!d_digests || (!d_elems && felts_per_msg)) return ANEMOI_B200_ERR_ARG;
+    return launch(field, inst, anemoi::MODE_HASH, d_elems, d_digests, nullptr, n_msgs, felts_per_msg, (cudaStream_t)stream);
+}
+
+int anemoi_b200_hash_field_ragged_dev(int field, int inst, const uint64_t* d_elems, const uint64_t* d_offsets,
+                                      size_t n_msgs, uint64_t* d_digests, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!d_digests || !d_offsets) return ANEMOI_B200_ERR_ARG;
+    return launch(field, inst, anemoi::MODE_HASH_RAGGED, d_elems, d_digests, d_offsets, n_msgs, 0, (cudaStream_t)stream);
+}
+
+int anemoi_b200_hash_bytes_dev(int field, int inst, const uint8_t* d_bytes, size_t n_msgs, size_t bytes_per_msg,
+                               uint64_t* d_digests, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!d_digests || (!d_bytes && bytes_per_msg)) return ANEMOI_B200_ERR_ARG;
+    return launch(field, inst, anemoi::MODE_HASH_BYTES, d_bytes, d_digests, nullptr, n_msgs, bytes_per_msg,
+                  (cudaStream_t)stream);
+}
+
+int anemoi_b200_merge_dev(int field, int inst, const uint64_t* d_pairs, uint64_t* d_out, size_t n, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!d_pairs || !d_out) return ANEMOI_B200_ERR_ARG;
+    const int mode = inst == ANEMOI_INST_2_1 ? anemoi::MODE_COMPRESS : anemoi::MODE_MERGE43;
+    return launch(field, inst, mode, d_pairs, d_out, nullptr, n, 0, (cudaStream_t)stream);
+}
+
+int anemoi_b200_digest_to_bytes_dev(int field, const uint64_t* d_digests, uint8_t* d_bytes, size_t n, void* stream) {
+    int rc = check_fi(field, ANEMOI_INST_2_1);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!d_digests || !d_bytes) return ANEMOI_B200_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_bytes) & 7) return ANEMOI_B200_ERR_ARG;
+    return launch(field, ANEMOI_INST_2_1, anemoi::MODE_TO_BYTES, d_digests, d_bytes, nullptr, n, 0, (cudaStream_t)stream);
+}
+
+size_t anemoi_b200_merkle_scratch_felts(int arity, size_t n_leaves) {
+    if (arity < 2) return 0;
+    const size_t l1 = n_leaves / (size_t)arity;
+    return l1 + l1 / (size_t)arity + 2;
+}
+
+int anemoi_b200_merkle_reduce_dev(int field, int inst, int arity, const uint64_t* d_leaves, size_t n_leaves, int levels,
+                                  uint64_t* d_scratch, uint64_t* d_out, void* stream) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    if (levels < 0) return ANEMOI_B200_ERR_ARG;
+    if (n_leaves == 0) return ANEMOI_B200_ERR_LENGTH;
+    size_t div = 1;
+    for (int l = 0; l < levels; l++) {
+        if (div > n_leaves / (size_t)arity) return ANEMOI_B200_ERR_LENGTH;
+        div *= (size_t)arity;
+    }
+    if (n_leaves % div != 0) return ANEMOI_B200_ERR_LENGTH;
+    if (!d_leaves || !d_out) return ANEMOI_B200_ERR_ARG;
+    if (levels > 1 && !d_scratch) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (levels == 0) {
+        CK(cudaMemcpyAsync(d_out, d_leaves, n_leaves * fb, cudaMemcpyDeviceToDevice, st));
+        return ANEMOI_B200_OK;
+    }
+    const int mode = arity == 2 ? anemoi::MODE_COMPRESS : anemoi::MODE_COMPRESS4;
+    const size_t words = (size_t)kFieldLimbs[field];
+    uint64_t* ping = d_scratch;                                      // n/arity felts
+    uint64_t* pong = d_scratch ? d_scratch + (n_leaves / arity + 1) * words : nullptr;  // n/arity^2 felts
+    const uint64_t* src = d_leaves;
+    size_t n = n_leaves;
+    for (int l = 0; l < levels; l++) {
+        const size_t nodes = n / (size_t)arity;
+        uint64_t* dst = (l == levels - 1) ? d_out : ((l & 1) ? pong : ping);
+        rc = launch(field, inst, mode, src, dst, nullptr, nodes, 0, st);
+        if (rc) return rc;
+        src = dst;
+        n = nodes;
+    }
+    return ANEMOI_B200_OK;
+}
+
+// ---- host-pointer entry points -----------------------------------------------------------------
+
+int anemoi_b200_permute(int field, int inst, uint64_t* states, size_t n, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!states) return ANEMOI_B200_ERR_ARG;
+    const size_t bytes = n * width_of(inst) * felt_bytes(field);
+    return host_call(device, states, bytes, states, bytes, true, [&](void* di, void*, cudaStream_t st) {
+        return anemoi_b200_permute_dev(field, inst, (uint64_t*)di, n, st);
+    });
+}
+
+int anemoi_b200_sbox_layer(int field, int inst, uint64_t* states, size_t n, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!states) return ANEMOI_B200_ERR_ARG;
+    const size_t bytes = n * width_of(inst) * felt_bytes(field);
+    return host_call(device, states, bytes, states, bytes, true, [&](void* di, void*, cudaStream_t st) {
+        return anemoi_b200_sbox_layer_dev(field, inst, (uint64_t*)di, n, st);
+    });
+}
+
+int anemoi_b200_compress(int field, int inst, int k, const uint64_t* in, uint64_t* out, size_t n, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    int per = 0;
+    int mode = jive_mode(inst, k, &per);
+    if (mode < 0) return mode;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!in || !out) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    return host_call(device, in, n * width_of(inst) * fb, out, n * per * fb, false, [&](void* di, void* dout, cudaStream_t st) {
+        return anemoi_b200_compress_dev(field, inst, k, (const uint64_t*)di, (uint64_t*)dout, n, st);
+    });
+}
+
+int anemoi_b200_hash_field(int field, int inst, const uint64_t* elems, size_t n_msgs, size_t felts_per_msg,
+                           uint64_t* digests, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!digests || (!elems && felts_per_msg)) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    return host_call(device, elems, n_msgs * felts_per_msg * fb, digests, n_msgs * fb, false,
+                     [&](void* di, void* dout, cudaStream_t st) {
+                         return anemoi_b200_hash_field_dev(field, inst, (const uint64_t*)di, n_msgs, felts_per_msg,
+                                                           (uint64_t*)dout, st);
+                     });
+}
+
+int anemoi_b200_hash_field_ragged(int field, int inst, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs,
+                                  uint64_t* digests, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!digests || !offsets) return ANEMOI_B200_ERR_ARG;
+    for (size_t i = 0; i < n_msgs; i++)
+        if (offsets[i + 1] < offsets[i]) return ANEMOI_B200_ERR_LENGTH;
+    const uint64_t base = offsets[0], total = offsets[n_msgs] - base;
+    if (total && !elems) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    // rebase the offsets so only the referenced element range is copied
+    std::vector<uint64_t> rel(n_msgs + 1);
+    for (size_t i = 0; i <= n_msgs; i++) rel[i] = offsets[i] - base;
+    DevBuf d_off;
+    CK(d_off.alloc((n_msgs + 1) * sizeof(uint64_t)));
+    CK(cudaMemcpy(d_off.p, rel.data(), (n_msgs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(elems) + base * fb;
+    return host_call(device, total ? src : reinterpret_cast<const uint8_t*>(rel.data()), total * fb, digests, n_msgs * fb,
+                     false, [&](void* di, void* dout, cudaStream_t st) {
+                         return anemoi_b200_hash_field_ragged_dev(field, inst, (const uint64_t*)di,
+                                                                  (const uint64_t*)d_off.p, n_msgs, (uint64_t*)dout, st);
+                     });
+}
+
+int anemoi_b200_hash_bytes(int field, int inst, const uint8_t* bytes, size_t n_msgs, size_t bytes_per_msg,
+                           uint64_t* digests, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!digests || (!bytes && bytes_per_msg)) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    return host_call(device, bytes_per_msg ? (const void*)bytes : (const void*)digests, n_msgs * bytes_per_msg, digests,
+                     n_msgs * fb, false, [&](void* di, void* dout, cudaStream_t st) {
+                         return anemoi_b200_hash_bytes_dev(field, inst, (const uint8_t*)di, n_msgs, bytes_per_msg,
+                                                           (uint64_t*)dout, st);
+                     });
+}
+
+int anemoi_b200_merge(int field, int inst, const uint64_t* digest_pairs, uint64_t* out, size_t n, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!digest_pairs || !out) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    return host_call(device, digest_pairs, n * 2 * fb, out, n * fb, false, [&](void* di, void* dout, cudaStream_t st) {
+        return anemoi_b200_merge_dev(field, inst, (const uint64_t*)di, (uint64_t*)dout, n, st);
+    });
+}
+
+int anemoi_b200_digest_to_bytes(int field, const uint64_t* digests, uint8_t* bytes, size_t n, int device) {
+    int rc = check_fi(field, ANEMOI_INST_2_1);
+    if (rc) return rc;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!digests || !bytes) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    return host_call(device, digests, n * fb, bytes, n * fb, false, [&](void* di, void* dout, cudaStream_t st) {
+        return anemoi_b200_digest_to_bytes_dev(field, (const uint64_t*)di, (uint8_t*)dout, n, st);
+    });
+}
+
+int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves, uint64_t* root,
+                            int n_gpus) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    if (n_leaves == 0) return ANEMOI_B200_ERR_LENGTH;
+    int height = 0;
+    {
+        size_t m = n_leaves;
+        while (m > 1) {
+            if (m % (size_t)arity) return ANEMOI_B200_ERR_LENGTH;  // must be arity^h
+            m /= (size_t)arity;
+            height++;
+        }
+    }
+    if (!leaves || !root) return ANEMOI_B200_ERR_ARG;
+    if (n_gpus < 1 || (n_gpus & (n_gpus - 1))) return ANEMOI_B200_ERR_ARG;
+    const int count = anemoi_b200_device_count();
+    if (count == 0) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "no CUDA device");
+        return ANEMOI_B200_ERR_NO_DEVICE;
+    }
+    if (n_gpus > count) return ANEMOI_B200_ERR_ARG;
+    if ((size_t)n_gpus > n_leaves) n_gpus = 1;
+    const size_t fb = felt_bytes(field);
+    const size_t words = (size_t)kFieldLimbs[field];
+    // each GPU reduces its contiguous slice as far as whole sub-trees allow
+    const size_t slice = n_leaves / (size_t)n_gpus;
+    int local_levels = 0;
+    {
+        size_t m = slice;
+        while (m > 1 && m % (size_t)arity == 0) {
+            m /= (size_t)arity;
+            local_levels++;
+        }
+    }
+    size_t roots_per_gpu = slice;
+    for (int l = 0; l < local_levels; l++) roots_per_gpu /= (size_t)arity;
+    const size_t n_partial = roots_per_gpu * (size_t)n_gpus;
+    std::vector<uint64_t> partial(n_partial * words);
+    std::vector<int> rcs(n_gpus, ANEMOI_B200_OK);
+    std::vector<std::string> errs(n_gpus);
+
+    auto worker = [&](int g) {
+        rcs[g] = [&]() -> int {
+            DeviceScope scope(g);
+            if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+            DevBuf d_leaves, d_scratch, d_out;
+            CK(d_leaves.alloc(slice * fb));
+            CK(d_scratch.alloc(anemoi_b200_merkle_scratch_felts(arity, slice) * fb));
+            CK(d_out.alloc(roots_per_gpu * fb));
+            cudaStream_t st;
+            CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            int r = ANEMOI_B200_OK;
+            cudaError_t e = cudaMemcpyAsync(d_leaves.p, leaves + (size_t)g * slice * words, slice * fb, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) r = cuda_fail(e, "H2D leaves");
+            if (!r)
+                r = anemoi_b200_merkle_reduce_dev(field, inst, arity, (const uint64_t*)d_leaves.p, slice, local_levels,
+                                                  (uint64_t*)d_scratch.p, (uint64_t*)d_out.p, st);
+            if (!r) {
+                e = cudaMemcpyAsync(partial.data() + (size_t)g * roots_per_gpu * words, d_out.p, roots_per_gpu * fb,
+                                    cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) r = cuda_fail(e, "D2H partial roots");
+            }
+            e = cudaStreamSynchronize(st);
+            if (!r && e != cudaSuccess) r = cuda_fail(e, "cudaStreamSynchronize");
+            cudaStreamDestroy(st);
+            return r;
+        }();
+        errs[g] = g_cuda_err;
+    };
+    if (n_gpus == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_gpus; g++) th.emplace_back(worker, g);
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < n_gpus; g++)
+        if (rcs[g]) {
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "gpu %d: %s", g, errs[g].c_str());
+            return rcs[g];
+        }
+    if (n_partial == 1) {
+        memcpy(root, partial.data(), fb);
+        return ANEMOI_B200_OK;
+    }
+    // top of the tree on device 0
+    const int top_levels = height - local_levels;
+    DeviceScope scope(0);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    DevBuf d_scratch;
+    CK(d_scratch.alloc(anemoi_b200_merkle_scratch_felts(arity, n_partial) * fb));
+    return host_call(0, partial.data(), n_partial * fb, root, fb, false, [&](void* di, void* dout, cudaStream_t st) {
+        return anemoi_b200_merkle_reduce_dev(field, inst, arity, (const uint64_t*)di, n_partial, top_levels,
+                                             (uint64_t*)d_scratch.p, (uint64_t*)dout, st);
+    });
+}
+
+}  // extern "C"

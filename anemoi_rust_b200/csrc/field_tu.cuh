@@ -1,0 +1,41 @@
+// Body of one per-field translation unit: instantiates anemoi_kernel<F, 1> (Anemoi-2-1) and
+// anemoi_kernel<F, 2> (Anemoi-4-3) for the field selected by ANEMOI_TU_FIELD and exports one launcher.
+// Each field is its own TU so that nvcc compiles the seven of them in parallel and each gets its own
+// constant bank for the ARK tables.
+#pragma once
+#include "anemoi_kernels.cuh"
+#include "launch.h"
+
+namespace anemoi {
+
+template <class F, int COLS>
+static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
+    if (a.n == 0) return cudaSuccess;
+    const unsigned long long threads = a.n * COLS;
+    // Big batches: 128-thread blocks (4 resident per SM). Small batches (upper Merkle levels, KATs): one
+    // warp per block so the few warps spread over all SMs and each gets an integer pipe to itself.
+    int device = 0, sms = 148;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int block = (threads >= (unsigned long long)sms * kBlockThreads * 2) ? kBlockThreads : 32;
+    const unsigned long long blocks = (threads + block - 1) / block;
+    if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)F::TABLE * F::N * sizeof(uint32_t) * block;
+    static bool attr_set[64] = {};
+    if (device < 64 && !attr_set[device]) {
+        cudaError_t e = cudaFuncSetAttribute(anemoi_kernel<F, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)((size_t)F::TABLE * F::N * sizeof(uint32_t) * kBlockThreads));
+        if (e != cudaSuccess) return e;
+        attr_set[device] = true;
+    }
+    anemoi_kernel<F, COLS><<<(unsigned)blocks, block, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace anemoi
+
+#define ANEMOI_DEFINE_LAUNCHER(FIELD)                                                                 \
+    extern "C" cudaError_t anemoi_launch_##FIELD(int cols, const anemoi::KernelArgs* a, cudaStream_t s) { \
+        return cols == 1 ? anemoi::launch_one<anemoi::F_##FIELD, 1>(*a, s)                               \
+                         : anemoi::launch_one<anemoi::F_##FIELD, 2>(*a, s);                              \
+    }

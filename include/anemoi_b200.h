@@ -1,0 +1,157 @@
+/*
+ * anemoi_b200.h -- C ABI of libanemoi_b200.so, the B200 (sm_100a) batched Anemoi engine.
+ *
+ * This is the drop-in boundary for the batched hot path of anemoi-hash/anemoi-rust. The reference has
+ * no FFI of its own: its API is per-item trait functions on zero-sized types. Each entry point below
+ * is the batched form of one of those functions and cites the reference item it replaces (paths are
+ * relative to the reference crate root). INTEGRATION.md shows the Rust `extern "C"` block and the
+ * extension traits a maintainer adds to bind them.
+ *
+ * DATA LAYOUT (identical to a Rust `&[Felt]` slice of arkworks `Fp<MontBackend<_, N>, N>`):
+ *   field element  = N64 little-endian u64 limbs (N64 = 6 for bls12_377/bls12_381, else 4),
+ *                    holding a * 2^(64*N64) mod p (Montgomery form), canonical (< p);
+ *   state          = W consecutive elements [x_0..x_{c-1}, y_0..y_{c-1}]  (W = 2: Anemoi-2-1, W = 4: Anemoi-4-3);
+ *   batch          = n consecutive states / digests, no padding.
+ * Inputs >= p are not checked (an arkworks Fp cannot hold them): no UB, result unspecified.
+ *
+ * OWNERSHIP / THREADING: the caller owns every buffer; the library borrows it for the duration of the
+ * call. Host-pointer calls are synchronous (H2D, kernels, D2H inside the call). `_dev` calls take
+ * device pointers on the CURRENT device and are ordered on `stream` (a cudaStream_t passed as void*;
+ * NULL = legacy default stream); they do not synchronize. All calls are re-entrant and thread-safe.
+ *
+ * ERRORS: 0 on success, a negative ANEMOI_B200_ERR_* otherwise. The reference panics (assert!) on bad
+ * lengths / arities; the ABI returns ERR_LENGTH / ERR_ARITY for the same conditions and never aborts.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry returns ERR_NO_DEVICE.
+ */
+#ifndef ANEMOI_B200_H
+#define ANEMOI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANEMOI_B200_VERSION 100 /* 0.1.0 */
+
+/* field ids: module order of src/lib.rs:27-64 */
+#define ANEMOI_FIELD_BLS12_377 0       /* src/bls12_377/mod.rs:1        ark_bls12_377::Fq, 6 limbs */
+#define ANEMOI_FIELD_BLS12_381 1       /* src/bls12_381/mod.rs:1        ark_bls12_381::Fq, 6 limbs */
+#define ANEMOI_FIELD_BN_254 2          /* src/bn_254/mod.rs:1           ark_bn254::Fq,     4 limbs */
+#define ANEMOI_FIELD_ED_ON_BLS12_377 3 /* src/ed_on_bls12_377/mod.rs:1  ark_bls12_377::Fr, 4 limbs */
+#define ANEMOI_FIELD_JUBJUB 4          /* src/jubjub/mod.rs:1           ark_bls12_381::Fr, 4 limbs */
+#define ANEMOI_FIELD_PALLAS 5          /* src/pallas/mod.rs:3           ark_pallas::Fq,    4 limbs */
+#define ANEMOI_FIELD_VESTA 6           /* src/vesta/mod.rs:3            ark_pallas::Fr,    4 limbs */
+#define ANEMOI_NUM_FIELDS 7
+
+/* instantiation ids */
+#define ANEMOI_INST_2_1 0 /* src/<field>/anemoi_2_1/mod.rs:20-38: width 2, rate 1, 1 column  */
+#define ANEMOI_INST_4_3 1 /* src/<field>/anemoi_4_3/mod.rs:20-38: width 4, rate 3, 2 columns */
+
+#define ANEMOI_B200_OK 0
+#define ANEMOI_B200_ERR_ARG (-1)       /* null pointer, bad device index, bad variant */
+#define ANEMOI_B200_ERR_FIELD (-2)     /* field id out of range */
+#define ANEMOI_B200_ERR_INST (-3)      /* instantiation id out of range */
+#define ANEMOI_B200_ERR_ARITY (-4)     /* k / arity the reference asserts against (hasher.rs:107, 4-3 :163-165) */
+#define ANEMOI_B200_ERR_LENGTH (-5)    /* length not a whole number of states / not a power of the arity */
+#define ANEMOI_B200_ERR_CUDA (-6)      /* a CUDA runtime call failed; see anemoi_b200_last_cuda_error() */
+#define ANEMOI_B200_ERR_NO_DEVICE (-7) /* no CUDA device: there is no CPU fallback */
+#define ANEMOI_B200_ERR_NOMEM (-8)     /* device or pinned-host allocation failed */
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int anemoi_b200_version(void);
+const char* anemoi_b200_strerror(int code);
+const char* anemoi_b200_last_cuda_error(void); /* text of the calling thread's last CUDA failure */
+int anemoi_b200_device_count(void);            /* 0 when there is no usable device */
+int anemoi_b200_field_limbs(int field);        /* N64 (4 or 6), or ERR_FIELD */
+int anemoi_b200_state_width(int inst);         /* STATE_WIDTH: 2 or 4 (src/<field>/anemoi_x/mod.rs:20) */
+int anemoi_b200_rate_width(int inst);          /* RATE_WIDTH: 1 or 3 (mod.rs:22) */
+int anemoi_b200_num_rounds(int field, int inst); /* NUM_HASH_ROUNDS (mod.rs:31-32) */
+const char* anemoi_b200_field_name(int field); /* "bls12_377", ... (src/lib.rs module names) */
+
+/* ---- host-pointer entry points (synchronous) ----------------------------------------------- */
+
+/* Anemoi::permutation (src/traits.rs:370-378) on n states, in place. */
+int anemoi_b200_permute(int field, int inst, uint64_t* states, size_t n, int device);
+
+/* Anemoi::sbox_layer (src/traits.rs:328-358) on n states, in place. Diagnostic entry: it is what the
+ * reference's test_sbox vectors (src/<field>/anemoi_x/mod.rs test_sbox) pin. */
+int anemoi_b200_sbox_layer(int field, int inst, uint64_t* states, size_t n, int device);
+
+/* Jive::compress / Jive::compress_k on n states.
+ *   inst 2-1: k must be 2 (src/<field>/anemoi_2_1/hasher.rs:96-110); out = n elements.
+ *   inst 4-3: k in {2, 4} (src/<field>/anemoi_4_3/hasher.rs:148-179); out = n * (4/k) elements.
+ * k = 2 is Jive::compress. Any other k -> ERR_ARITY (the reference panics). */
+int anemoi_b200_compress(int field, int inst, int k, const uint64_t* in, uint64_t* out, size_t n, int device);
+
+/* Sponge::hash_field (2-1: src/<field>/anemoi_2_1/hasher.rs:68-85; 4-3: anemoi_4_3/hasher.rs:93-129)
+ * on n_msgs messages of felts_per_msg elements each (message i at elems[i*felts_per_msg ...]).
+ * digests = n_msgs elements. felts_per_msg may be 0. */
+int anemoi_b200_hash_field(int field, int inst, const uint64_t* elems, size_t n_msgs, size_t felts_per_msg,
+                           uint64_t* digests, int device);
+
+/* Ragged form: message i is elems[offsets[i] .. offsets[i+1]) (element indices; n_msgs + 1 offsets,
+ * non-decreasing, offsets[0] may be non-zero). */
+int anemoi_b200_hash_field_ragged(int field, int inst, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs,
+                                  uint64_t* digests, int device);
+
+/* Sponge::hash (2-1: anemoi_2_1/hasher.rs:18-66; 4-3: anemoi_4_3/hasher.rs:18-91) on n_msgs byte
+ * strings of bytes_per_msg bytes each: 31- (47-) byte little-endian chunks, the 0x01 pad rule, and the
+ * canonical -> Montgomery conversion all happen on the device. */
+int anemoi_b200_hash_bytes(int field, int inst, const uint8_t* bytes, size_t n_msgs, size_t bytes_per_msg,
+                           uint64_t* digests, int device);
+
+/* Sponge::merge on n digest pairs (in = 2n elements, out = n elements).
+ *   2-1: Jive compress (anemoi_2_1/hasher.rs:87-92).
+ *   4-3: the reference's sponge merge, which copies digests[0] twice and never reads digests[1]
+ *        (anemoi_4_3/hasher.rs:131-144) -- reproduced literally. */
+int anemoi_b200_merge(int field, int inst, const uint64_t* digest_pairs, uint64_t* out, size_t n, int device);
+
+/* Jive Merkle root (the reference has no tree code; node function = its Jive compress):
+ *   arity 2 on inst 2-1: node = compress([l, r]);  arity 4 on inst 4-3: node = compress_k([a,b,c,d], 4).
+ * n_leaves must be arity^h, h >= 0 (h = 0: root = the leaf). Built level by level on the device;
+ * n_gpus > 1 splits the leaves into n_gpus contiguous slices (n_gpus must be a power of two <=
+ * device_count and divide n_leaves into whole sub-trees or whole groups of sub-trees), reduces each
+ * slice on its own GPU concurrently, gathers the partial roots and finishes on device 0. */
+int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves, uint64_t* root,
+                            int n_gpus);
+
+/* AnemoiDigest::to_bytes (src/<field>/anemoi_x/digest.rs:42-46): n Montgomery elements -> n canonical
+ * little-endian byte strings of 8*N64 bytes each (de-Montgomery on the device). */
+int anemoi_b200_digest_to_bytes(int field, const uint64_t* digests, uint8_t* bytes, size_t n, int device);
+
+/* ---- device-pointer, stream-ordered entry points (current device) -------------------------- */
+int anemoi_b200_permute_dev(int field, int inst, uint64_t* d_states, size_t n, void* stream);
+int anemoi_b200_sbox_layer_dev(int field, int inst, uint64_t* d_states, size_t n, void* stream);
+int anemoi_b200_compress_dev(int field, int inst, int k, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream);
+int anemoi_b200_hash_field_dev(int field, int inst, const uint64_t* d_elems, size_t n_msgs, size_t felts_per_msg,
+                               uint64_t* d_digests, void* stream);
+int anemoi_b200_hash_field_ragged_dev(int field, int inst, const uint64_t* d_elems, const uint64_t* d_offsets,
+                                      size_t n_msgs, uint64_t* d_digests, void* stream);
+int anemoi_b200_hash_bytes_dev(int field, int inst, const uint8_t* d_bytes, size_t n_msgs, size_t bytes_per_msg,
+                               uint64_t* d_digests, void* stream);
+int anemoi_b200_merge_dev(int field, int inst, const uint64_t* d_pairs, uint64_t* d_out, size_t n, void* stream);
+int anemoi_b200_digest_to_bytes_dev(int field, const uint64_t* d_digests, uint8_t* d_bytes, size_t n, void* stream);
+
+/* Reduce `levels` levels of a Jive Merkle tree on the device: d_leaves (n_leaves elements, not
+ * modified) -> d_out (n_leaves / arity^levels elements). d_scratch must hold at least
+ * anemoi_b200_merkle_scratch_felts(arity, n_leaves) elements (it may be NULL when levels <= 1).
+ * n_leaves must be a multiple of arity^levels. This is the per-GPU leg of a sharded tree: each rank
+ * reduces its slice to its partial roots, the ranks all-gather them (NCCL), and every rank finishes the
+ * top levels with one more call. */
+int anemoi_b200_merkle_reduce_dev(int field, int inst, int arity, const uint64_t* d_leaves, size_t n_leaves, int levels,
+                                  uint64_t* d_scratch, uint64_t* d_out, void* stream);
+size_t anemoi_b200_merkle_scratch_felts(int arity, size_t n_leaves);
+
+/* ---- roofline denominator ------------------------------------------------------------------ */
+/* Chip-wide issue rate of one integer-multiply flavour on the current device, measured with
+ * independent chains. variant: 0 mad.lo.u32, 1 mad.hi.u32, 2 mad.wide.u32, 3 carry-chained
+ * mad.lo.cc/madc.hi.cc pairs (= IMAD.WIDE.U32.X, what the kernels issue), 4 = 3 with co-issued IADD3,
+ * 5 fma.rn.f64 (context). ops_per_s = instructions (MAC32 for 2-4) per second; sm_mhz = SM clock seen. */
+int anemoi_b200_imad_peak(int variant, double* ops_per_s, double* sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANEMOI_B200_H */
