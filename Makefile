@@ -1,7 +1,7 @@
 # Builds libanemoi_b200.so (sm_100a only), the C oracle, and the standalone IMAD microbenchmark.
 NVCC      ?= nvcc
-CXX       ?= g++
-CC        ?= gcc
+CXX       := g++
+CC        := gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -Iinclude -Xcompiler -fPIC -Xptxas -v
 CSRC      := anemoi_rust_b200/csrc
@@ -24,7 +24,7 @@ tools/imad_peak: tools/imad_peak_main.cu $(LIB)
 	$(NVCC) -std=c++17 -O3 $(ARCH) -Iinclude -o $@ tools/imad_peak_main.cu -Lanemoi_rust_b200 -lanemoi_b200 -Xlinker -rpath='$$ORIGIN/../anemoi_rust_b200'
 
 oracle/libanemoi_oracle.so: oracle/anemoi_oracle.c oracle/params_gen.h
-	$(CC) -O3 -march=x86-64-v3 -fopenmp -shared -fPIC -o $@ oracle/anemoi_oracle.c
+	$(CC) -O3 -funroll-loops -march=x86-64-v3 -fopenmp -shared -fPIC -o $@ oracle/anemoi_oracle.c
 
 clean:
 	rm -rf build $(LIB) oracle/libanemoi_oracle.so tools/imad_peak
