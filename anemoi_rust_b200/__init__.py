@@ -7,6 +7,7 @@ from .ffi import AnemoiError, ArityError, LengthError, NoDeviceError
 from .fields import FIELDS, FIELD_NAMES, INST_2_1, INST_4_3
 from .hasher import *  # noqa: F401,F403  (AnemoiBls12_381_2_1, ..., AnemoiDigest, HASHERS)
 from .hasher import HASHERS, AnemoiDigest
+from . import merkle
 
 __version__ = "0.1.0"
 

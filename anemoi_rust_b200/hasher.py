@@ -178,9 +178,10 @@ class _AnemoiBase:
         return cls.compress_k_batch(states, 2, out)
 
     @classmethod
-    def hash_field_batch(cls, elems, felts_per_msg=None, offsets=None):
+    def hash_field_batch(cls, elems, felts_per_msg=None, offsets=None, n_msgs=None):
         """Sponge::hash_field on many messages. Either elems has shape (n_msgs, L, N64) / felts_per_msg is
-        given (fixed length), or `offsets` (n_msgs + 1 element offsets) describes ragged messages."""
+        given (fixed length; pass n_msgs too when felts_per_msg == 0), or `offsets` (n_msgs + 1 element
+        offsets) describes ragged messages."""
         f = cls.FIELD
         if _is_torch(elems):
             import torch
@@ -197,7 +198,7 @@ class _AnemoiBase:
             if felts_per_msg is None:
                 assert t.dim() == 3
                 felts_per_msg = t.shape[1]
-            n = t.numel() // (felts_per_msg * f.n64) if felts_per_msg else t.shape[0]
+            n = t.numel() // (felts_per_msg * f.n64) if felts_per_msg else (n_msgs or 0)
             out = torch.empty((n, f.n64), dtype=t.dtype, device=t.device)
             ffi.check(_lib.anemoi_b200_hash_field_dev(f.id, cls.INST, ctypes.c_void_p(t.data_ptr()), n, felts_per_msg,
                                                       ctypes.c_void_p(out.data_ptr()), _stream_of(t)))
@@ -214,8 +215,10 @@ class _AnemoiBase:
             felts_per_msg = a.shape[1]
             n = a.shape[0]
         else:
-            n = a.size // (felts_per_msg * f.n64) if felts_per_msg else 0
+            n = a.size // (felts_per_msg * f.n64) if felts_per_msg else (n_msgs or 0)
         out = np.empty((n, f.n64), dtype=np.uint64)
+        if a.size == 0:
+            a = np.zeros(f.n64, dtype=np.uint64)
         ffi.check(_lib.anemoi_b200_hash_field(f.id, cls.INST, _ptr(a), n, felts_per_msg, _ptr(out), cls.device))
         return out
 

@@ -1,0 +1,96 @@
+"""Jive Merkle trees on device, single- and multi-GPU (one process per GPU, torch.distributed).
+
+The reference has no tree code; the node function is its Jive compression (arity 2: Anemoi-2-1
+`compress`, src/<field>/anemoi_2_1/hasher.rs:96-103; arity 4: Anemoi-4-3 `compress_k(.,4)`,
+anemoi_4_3/hasher.rs:162-179), iterated level by level, left to right.
+
+Sharding: rank g holds leaves [g*n/G, (g+1)*n/G), reduces its slice while it still
+consists of whole sub-trees (no communication), then ONE all-gather of the partial roots (<= a few
+hundred bytes) and every rank finishes the top levels redundantly. PyTorch is only plumbing here
+(device buffers, streams, the process group); all hashing is the CUDA kernels behind the C ABI."""
+import ctypes
+
+from . import ffi
+
+_lib = ffi.lib
+
+
+def plan(n_leaves, arity, world_size):
+    """Host logic of the sharded build. Returns (slice_len, local_levels, roots_per_rank, top_levels)."""
+    if n_leaves < 1 or world_size < 1:
+        raise ffi.LengthError(ffi.ERR_LENGTH, "empty tree")
+    height, m = 0, n_leaves
+    while m > 1:
+        if m % arity:
+            raise ffi.LengthError(ffi.ERR_LENGTH, "n_leaves must be a power of the arity")
+        m //= arity
+        height += 1
+    if n_leaves % world_size:
+        raise ffi.LengthError(ffi.ERR_LENGTH, "n_leaves must be divisible by the number of ranks")
+    slice_len = n_leaves // world_size
+    local_levels, m = 0, slice_len
+    while m > 1 and m % arity == 0:
+        m //= arity
+        local_levels += 1
+    roots_per_rank = m
+    total = roots_per_rank * world_size
+    # the gathered partial roots must themselves form a complete tree
+    top_levels, t = 0, total
+    while t > 1:
+        if t % arity:
+            raise ffi.LengthError(ffi.ERR_LENGTH, "world size does not split this tree into whole sub-trees")
+        t //= arity
+        top_levels += 1
+    assert local_levels + top_levels == height
+    return slice_len, local_levels, roots_per_rank, top_levels
+
+
+def merkle_reduce(H, leaves, levels, scratch=None, out=None):
+    """Reduce `levels` levels on the current device. leaves: CUDA int64/uint64 tensor (n, N64)."""
+    import torch
+
+    f, arity = H.FIELD, H.STATE_WIDTH
+    n = leaves.numel() // f.n64
+    if n == 0 or n % (arity ** levels):
+        raise ffi.LengthError(ffi.ERR_LENGTH, "n_leaves is not a multiple of arity^levels")
+    n_out = n // (arity ** levels)
+    if out is None:
+        out = torch.empty((n_out, f.n64), dtype=leaves.dtype, device=leaves.device)
+    if scratch is None:
+        scratch = torch.empty((_lib.anemoi_b200_merkle_scratch_felts(arity, n), f.n64), dtype=leaves.dtype,
+                              device=leaves.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(leaves.device).cuda_stream)
+    ffi.check(_lib.anemoi_b200_merkle_reduce_dev(f.id, H.INST, arity, ctypes.c_void_p(leaves.data_ptr()), n, levels,
+                                                 ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                 stream))
+    return out
+
+
+def merkle_root_device(H, leaves, scratch=None):
+    """Root of a device-resident tree on one GPU."""
+    f, arity = H.FIELD, H.STATE_WIDTH
+    n = leaves.numel() // f.n64
+    _, levels, roots, _ = plan(n, arity, 1)
+    assert roots == 1
+    return merkle_reduce(H, leaves, levels, scratch=scratch)
+
+
+def merkle_root_distributed(H, local_leaves, group=None, reduce_fn=None, scratch=None):
+    """Sharded root: every rank passes its contiguous slice; returns the (identical) root on every rank.
+    `reduce_fn(H, tensor, levels)` is injectable so the host logic (plan + all-gather + top levels) can be
+    exercised on CPU/gloo in tests; the product path always uses the CUDA `merkle_reduce`."""
+    import torch
+    import torch.distributed as dist
+
+    reduce_fn = reduce_fn or merkle_reduce
+    f, arity = H.FIELD, H.STATE_WIDTH
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n_local = local_leaves.numel() // f.n64
+    _, local_levels, roots_per_rank, top_levels = plan(n_local * world, arity, world)
+    kw = {"scratch": scratch} if (scratch is not None and reduce_fn is merkle_reduce) else {}
+    part = reduce_fn(H, local_leaves, local_levels, **kw)
+    if world == 1:
+        return part if top_levels == 0 else reduce_fn(H, part, top_levels)
+    gathered = torch.empty((world * roots_per_rank, f.n64), dtype=part.dtype, device=part.device)
+    dist.all_gather_into_tensor(gathered, part.contiguous(), group=group)
+    return reduce_fn(H, gathered, top_levels)
