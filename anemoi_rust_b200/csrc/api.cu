@@ -91,14 +91,45 @@ int jive_mode(int inst, int k, int* out_per_state) {
     return ANEMOI_B200_ERR_ARITY;
 }
 
-// RAII device buffer / device selection for the host-pointer entry points
+// Device buffers of the host-pointer entry points come from the device's stream-ordered memory pool with
+// an unlimited release threshold, so repeated calls reuse the same HBM without cudaMalloc/cudaFree round
+// trips (those cost ~10 ms each at 100 MiB and would dominate the copy time).
 struct DevBuf {
     void* p = nullptr;
+    cudaStream_t st = nullptr;
+    bool async = false;
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (!p) return;
+        if (async) cudaFreeAsync(p, st);
+        else cudaFree(p);
     }
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    cudaError_t alloc_async(size_t bytes, cudaStream_t stream) {
+        st = stream;
+        async = true;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, stream);
+        if (e != cudaSuccess) {  // pool unsupported / exhausted: plain allocation
+            cudaGetLastError();
+            async = false;
+            p = nullptr;
+            e = cudaMalloc(&p, bytes ? bytes : 16);
+        }
+        return e;
+    }
 };
+
+void keep_pool_memory(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long threshold = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    } else {
+        cudaGetLastError();
+    }
+    done[device] = true;
+}
 
 struct DeviceScope {
     int prev = -1;
@@ -129,21 +160,28 @@ template <class Body>
 int host_call(int device, const void* in, size_t in_bytes, void* out, size_t out_bytes, bool in_place, Body body) {
     DeviceScope scope(device);
     if (scope.rc != ANEMOI_B200_OK) return scope.rc;
-    DevBuf d_in, d_out;
-    CK(d_in.alloc(in_bytes));
-    if (!in_place) CK(d_out.alloc(out_bytes));
+    keep_pool_memory(device);
     cudaStream_t stream;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = ANEMOI_B200_OK;
-    cudaError_t e = cudaMemcpyAsync(d_in.p, in, in_bytes, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) rc = cuda_fail(e, "H2D copy");
-    if (rc == ANEMOI_B200_OK) rc = body(d_in.p, in_place ? d_in.p : d_out.p, stream);
-    if (rc == ANEMOI_B200_OK) {
-        e = cudaMemcpyAsync(out, in_place ? d_in.p : d_out.p, out_bytes, cudaMemcpyDeviceToHost, stream);
-        if (e != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+    {
+        DevBuf d_in, d_out;  // freed (stream-ordered) before the stream is destroyed
+        cudaError_t e = d_in.alloc_async(in_bytes, stream);
+        if (e == cudaSuccess && !in_place) e = d_out.alloc_async(out_bytes, stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "device allocation");
+        if (rc == ANEMOI_B200_OK) {
+            e = cudaMemcpyAsync(d_in.p, in, in_bytes, cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "H2D copy");
+        }
+        if (rc == ANEMOI_B200_OK) rc = body(d_in.p, in_place ? d_in.p : d_out.p, stream);
+        if (rc == ANEMOI_B200_OK) {
+            e = cudaMemcpyAsync(out, in_place ? d_in.p : d_out.p, out_bytes, cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+        }
+        e = cudaStreamSynchronize(stream);
+        if (rc == ANEMOI_B200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
-    e = cudaStreamSynchronize(stream);
-    if (rc == ANEMOI_B200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
     return rc;
 }

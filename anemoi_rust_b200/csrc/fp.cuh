@@ -80,7 +80,8 @@ FPQ void subc(uint32_t& a, uint32_t b) { a = a - b - g_cc; }
 FPQ uint32_t shf_l(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (32 - s)); }
 #else
 FPQ void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
-    asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    // one IMAD.WIDE.U32 Rd, Ra, Rb, RZ (separate mul.lo / mul.hi would become IMAD + IMAD.HI: 2 + 6 pipe cycles)
+    asm volatile("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 FPQ uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 // {lo,hi} += a*b ; carry out
@@ -231,31 +232,69 @@ FPQ void madc_row_rshift(uint32_t* odd, const uint32_t* a, uint32_t b) {
     madc_wide_cc_to(odd[N - 2], odd[N - 1], a[N - 2], b, 0u, 0u);
 }
 
+// m * p rows with the modulus limbs as compile-time constants. Limbs that are 0, 1 or a power of two
+// (p[0] = 1 for five of the seven fields; Pallas/Vesta: p = 2^254 + t with p[4..6] = 0, p[7] = 2^30) do not
+// need a multiplier: they become add-with-carry / shift instructions on the ALU pipe, which is idle while the
+// FMA-heavy pipe is saturated by IMAD.WIDE. SPECIAL_LIMBS selects how many of them are diverted (balance
+// between the two pipes; 0 = all limbs go through IMAD.WIDE).
+HD constexpr bool fp_is_pow2(uint32_t v) { return v != 0 && (v & (v - 1)) == 0; }
+HD constexpr int fp_log2(uint32_t v) { return v <= 1 ? 0 : 1 + fp_log2(v >> 1); }
+
 template <class F>
 struct ModRow {
-    // the modulus as a strided "array": P(j) for even/odd starts
+    static constexpr int N = F::N;
+    // {lo,hi} (+)= P*m [+ carry]; carry out. FIRST: no carry in. TO: write {dlo,dhi} = P*m + {clo,chi}.
+    template <bool FIRST>
+    static FPQ void mac(uint32_t& lo, uint32_t& hi, int j, uint32_t m) {
+        const uint32_t P = F::p(j);
+        if (F::special_limb(j) && P == 0) {
+            if (FIRST) add_cc(lo, 0u); else addc_cc(lo, 0u);
+            addc_cc(hi, 0u);
+        } else if (F::special_limb(j) && P == 1) {
+            if (FIRST) add_cc(lo, m); else addc_cc(lo, m);
+            addc_cc(hi, 0u);
+        } else if (F::special_limb(j) && fp_is_pow2(P)) {
+            const int k = fp_log2(P);
+            if (FIRST) add_cc(lo, m << k); else addc_cc(lo, m << k);
+            addc_cc(hi, m >> (32 - k));
+        } else {
+            if (FIRST) mad_wide_cc(lo, hi, P, m); else madc_wide_cc(lo, hi, P, m);
+        }
+    }
+    static FPQ void mac_to(uint32_t& dlo, uint32_t& dhi, int j, uint32_t m, uint32_t clo, uint32_t chi) {
+        const uint32_t P = F::p(j);
+        if (F::special_limb(j) && P == 0) {
+            dlo = clo; dhi = chi;
+            addc_cc(dlo, 0u); addc_cc(dhi, 0u);
+        } else if (F::special_limb(j) && P == 1) {
+            dlo = clo; dhi = chi;
+            addc_cc(dlo, m); addc_cc(dhi, 0u);
+        } else if (F::special_limb(j) && fp_is_pow2(P)) {
+            const int k = fp_log2(P);
+            dlo = clo; dhi = chi;
+            addc_cc(dlo, m << k); addc_cc(dhi, m >> (32 - k));
+        } else {
+            madc_wide_cc_to(dlo, dhi, P, m, clo, chi);
+        }
+    }
     static FPQ void cmad_even(uint32_t* acc, uint32_t m) {
-        constexpr int N = F::N;
-        mad_wide_cc(acc[0], acc[1], F::p(0), m);
+        mac<true>(acc[0], acc[1], 0, m);
         FP_UNROLL
-        for (int j = 2; j < N; j += 2) madc_wide_cc(acc[j], acc[j + 1], F::p(j), m);
+        for (int j = 2; j < N; j += 2) mac<false>(acc[j], acc[j + 1], j, m);
     }
     static FPQ void cmad_odd(uint32_t* acc, uint32_t m) {
-        constexpr int N = F::N;
-        mad_wide_cc(acc[0], acc[1], F::p(1), m);
+        mac<true>(acc[0], acc[1], 1, m);
         FP_UNROLL
-        for (int j = 2; j < N; j += 2) madc_wide_cc(acc[j], acc[j + 1], F::p(j + 1), m);
+        for (int j = 2; j < N; j += 2) mac<false>(acc[j], acc[j + 1], j + 1, m);
     }
     static FPQ void mul_odd(uint32_t* acc, uint32_t m) {
-        constexpr int N = F::N;
         FP_UNROLL
         for (int j = 0; j < N; j += 2) mul_wide(acc[j], acc[j + 1], F::p(j + 1), m);
     }
     static FPQ void madc_odd_rshift(uint32_t* odd, uint32_t m) {
-        constexpr int N = F::N;
         FP_UNROLL
-        for (int j = 0; j < N - 2; j += 2) madc_wide_cc_to(odd[j], odd[j + 1], F::p(j + 1), m, odd[j + 2], odd[j + 3]);
-        madc_wide_cc_to(odd[N - 2], odd[N - 1], F::p(N - 1), m, 0u, 0u);
+        for (int j = 0; j < N - 2; j += 2) mac_to(odd[j], odd[j + 1], j + 1, m, odd[j + 2], odd[j + 3]);
+        mac_to(odd[N - 2], odd[N - 1], N - 1, m, 0u, 0u);
     }
 };
 
@@ -275,7 +314,7 @@ FPQ void mad_redc_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t
         cmad_row<N>(even, a, bi);
         addc(odd[N - 1], 0u);
     }
-    uint32_t m = mul_lo(even[0], F::N0INV);
+    uint32_t m = mul_lo(even[0], F::n0inv());
     ModRow<F>::cmad_odd(odd, m);
     ModRow<F>::cmad_even(even, m);
     addc(odd[N - 1], 0u);
@@ -314,13 +353,13 @@ template <class F>
 FPQ void redc_row(uint32_t* even, uint32_t* odd, bool first) {
     constexpr int N = F::N;
     if (first) {
-        uint32_t m = mul_lo(even[0], F::N0INV);
+        uint32_t m = mul_lo(even[0], F::n0inv());
         ModRow<F>::mul_odd(odd, m);
         ModRow<F>::cmad_even(even, m);
         addc(odd[N - 1], 0u);
     } else {
         add_cc(even[0], odd[1]);
-        uint32_t m = mul_lo(even[0], F::N0INV);  // mul.lo does not touch the carry flag
+        uint32_t m = mul_lo(even[0], F::n0inv());  // mul.lo does not touch the carry flag
         ModRow<F>::madc_odd_rshift(odd, m);
         ModRow<F>::cmad_even(even, m);
         addc(odd[N - 1], 0u);
