@@ -6,9 +6,9 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -Iinclude -Xcompiler -fPIC -Xptxas -v
 CSRC      := anemoi_rust_b200/csrc
 FIELDS    := bls12_377 bls12_381 bn_254 ed_on_bls12_377 jubjub pallas vesta
-OBJS      := $(patsubst %,build/field_%.o,$(FIELDS)) build/api.o build/imad_peak.o
+OBJS      := $(patsubst %,build/field_%.o,$(FIELDS)) build/api.o build/imad_peak.o build/merkle_aux.o
 LIB       := anemoi_rust_b200/libanemoi_b200.so
-HDRS      := $(CSRC)/fp.cuh $(CSRC)/anemoi_kernels.cuh $(CSRC)/field_tu.cuh $(CSRC)/launch.h $(CSRC)/kernel_args.h \
+HDRS      := $(CSRC)/fp.cuh $(CSRC)/anemoi_kernels.cuh $(CSRC)/field_tu.cuh $(CSRC)/launch.h $(CSRC)/kernel_args.h $(CSRC)/merkle_aux.h \
              $(CSRC)/generated/fields.cuh include/anemoi_b200.h
 
 all: $(LIB) oracle/libanemoi_oracle.so tools/imad_peak

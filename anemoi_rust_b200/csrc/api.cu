@@ -13,6 +13,7 @@
 #include "anemoi_b200.h"
 #include "kernel_args.h"
 #include "launch.h"
+#include "merkle_aux.h"
 
 namespace {
 
@@ -366,6 +367,95 @@ int anemoi_b200_merkle_reduce_dev(int field, int inst, int arity, const uint64_t
     return ANEMOI_B200_OK;
 }
 
+// ---- retained trees, openings, verification ------------------------------------------------------
+
+size_t anemoi_b200_merkle_tree_felts(int arity, size_t n_leaves) {
+    if (arity < 2 || n_leaves == 0) return 0;
+    return (n_leaves - 1) / (size_t)(arity - 1);
+}
+
+static int tree_height(int arity, size_t n_leaves, int* height) {
+    if (n_leaves == 0) return ANEMOI_B200_ERR_LENGTH;
+    int h = 0;
+    size_t m = n_leaves;
+    while (m > 1) {
+        if (m % (size_t)arity) return ANEMOI_B200_ERR_LENGTH;
+        m /= (size_t)arity;
+        h++;
+    }
+    *height = h;
+    return ANEMOI_B200_OK;
+}
+
+int anemoi_b200_merkle_tree_dev(int field, int inst, int arity, const uint64_t* d_leaves, size_t n_leaves,
+                                uint64_t* d_tree, void* stream) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    int height = 0;
+    rc = tree_height(arity, n_leaves, &height);
+    if (rc) return rc;
+    if (height == 0) return ANEMOI_B200_OK;  // a single leaf is its own root; the tree above it is empty
+    if (!d_leaves || !d_tree) return ANEMOI_B200_ERR_ARG;
+    const int mode = arity == 2 ? anemoi::MODE_COMPRESS : anemoi::MODE_COMPRESS4;
+    const size_t words = (size_t)kFieldLimbs[field];
+    const uint64_t* src = d_leaves;
+    uint64_t* dst = d_tree;
+    size_t n = n_leaves;
+    for (int l = 0; l < height; l++) {
+        const size_t nodes = n / (size_t)arity;
+        rc = launch(field, inst, mode, src, dst, nullptr, nodes, 0, (cudaStream_t)stream);
+        if (rc) return rc;
+        src = dst;
+        dst += nodes * words;
+        n = nodes;
+    }
+    return ANEMOI_B200_OK;
+}
+
+int anemoi_b200_merkle_open_dev(int field, int inst, int arity, const uint64_t* d_leaves, const uint64_t* d_tree,
+                                size_t n_leaves, const uint64_t* d_indices, size_t n_idx, uint64_t* d_paths, void* stream) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    int height = 0;
+    rc = tree_height(arity, n_leaves, &height);
+    if (rc) return rc;
+    if (n_idx == 0 || height == 0) return ANEMOI_B200_OK;
+    if (!d_leaves || !d_tree || !d_indices || !d_paths) return ANEMOI_B200_ERR_ARG;
+    CK(anemoi_aux_gather_paths(d_leaves, d_tree, n_leaves, arity, height, kFieldLimbs[field], d_indices, n_idx, d_paths,
+                               (cudaStream_t)stream));
+    return ANEMOI_B200_OK;
+}
+
+int anemoi_b200_merkle_verify_dev(int field, int inst, int arity, const uint64_t* d_leaf_values, const uint64_t* d_indices,
+                                  const uint64_t* d_paths, int height, size_t n_idx, uint64_t* d_scratch, uint64_t* d_roots,
+                                  void* stream) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    if (height < 0) return ANEMOI_B200_ERR_ARG;
+    if (n_idx == 0) return ANEMOI_B200_OK;
+    if (!d_leaf_values || !d_roots) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (height == 0) {
+        CK(cudaMemcpyAsync(d_roots, d_leaf_values, n_idx * fb, cudaMemcpyDeviceToDevice, st));
+        return ANEMOI_B200_OK;
+    }
+    if (!d_indices || !d_paths || !d_scratch) return ANEMOI_B200_ERR_ARG;
+    const int mode = arity == 2 ? anemoi::MODE_COMPRESS : anemoi::MODE_COMPRESS4;
+    const size_t words = (size_t)kFieldLimbs[field];
+    uint64_t* states = d_scratch;                          // n_idx * arity felts
+    uint64_t* cur = d_scratch + n_idx * (size_t)arity * words;  // n_idx felts
+    const uint64_t* src = d_leaf_values;
+    for (int l = 0; l < height; l++) {
+        CK(anemoi_aux_assemble_level(src, d_paths, d_indices, l, arity, height, (int)words, n_idx, states, st));
+        uint64_t* dst = (l == height - 1) ? d_roots : cur;
+        rc = launch(field, inst, mode, states, dst, nullptr, n_idx, 0, st);
+        if (rc) return rc;
+        src = dst;
+    }
+    return ANEMOI_B200_OK;
+}
+
 // ---- host-pointer entry points -----------------------------------------------------------------
 
 int anemoi_b200_permute(int field, int inst, uint64_t* states, size_t n, int device) {
@@ -577,6 +667,96 @@ int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leav
         return anemoi_b200_merkle_reduce_dev(field, inst, arity, (const uint64_t*)di, n_partial, top_levels,
                                              (uint64_t*)d_scratch.p, (uint64_t*)dout, st);
     });
+}
+
+int anemoi_b200_merkle_open(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves,
+                            const uint64_t* indices, size_t n_idx, uint64_t* root, uint64_t* paths, int device) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    int height = 0;
+    rc = tree_height(arity, n_leaves, &height);
+    if (rc) return rc;
+    if (!leaves || !root || (n_idx && (!indices || (height && !paths)))) return ANEMOI_B200_ERR_ARG;
+    for (size_t i = 0; i < n_idx; i++)
+        if (indices[i] >= n_leaves) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    if (height == 0) {
+        memcpy(root, leaves, fb);
+        return ANEMOI_B200_OK;
+    }
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    keep_pool_memory(device);
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    {
+        const size_t tree_felts = anemoi_b200_merkle_tree_felts(arity, n_leaves);
+        const size_t path_felts = n_idx * (size_t)height * (size_t)(arity - 1);
+        DevBuf d_leaves, d_tree, d_idx, d_paths;
+        cudaError_t e = d_leaves.alloc_async(n_leaves * fb, st);
+        if (e == cudaSuccess) e = d_tree.alloc_async(tree_felts * fb, st);
+        if (e == cudaSuccess) e = d_idx.alloc_async(n_idx * sizeof(uint64_t), st);
+        if (e == cudaSuccess) e = d_paths.alloc_async(path_felts * fb, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "device allocation");
+        if (!rc && (e = cudaMemcpyAsync(d_leaves.p, leaves, n_leaves * fb, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            rc = cuda_fail(e, "H2D leaves");
+        if (!rc && n_idx && (e = cudaMemcpyAsync(d_idx.p, indices, n_idx * sizeof(uint64_t), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            rc = cuda_fail(e, "H2D indices");
+        if (!rc) rc = anemoi_b200_merkle_tree_dev(field, inst, arity, (const uint64_t*)d_leaves.p, n_leaves, (uint64_t*)d_tree.p, st);
+        if (!rc)
+            rc = anemoi_b200_merkle_open_dev(field, inst, arity, (const uint64_t*)d_leaves.p, (const uint64_t*)d_tree.p, n_leaves,
+                                             (const uint64_t*)d_idx.p, n_idx, (uint64_t*)d_paths.p, st);
+        if (!rc && (e = cudaMemcpyAsync(root, (const uint8_t*)d_tree.p + (tree_felts - 1) * fb, fb, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            rc = cuda_fail(e, "D2H root");
+        if (!rc && path_felts && (e = cudaMemcpyAsync(paths, d_paths.p, path_felts * fb, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            rc = cuda_fail(e, "D2H paths");
+        e = cudaStreamSynchronize(st);
+        if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+int anemoi_b200_merkle_verify(int field, int inst, int arity, const uint64_t* leaf_values, const uint64_t* indices,
+                              const uint64_t* paths, int height, size_t n_idx, uint64_t* roots, int device) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    if (height < 0) return ANEMOI_B200_ERR_ARG;
+    if (n_idx == 0) return ANEMOI_B200_OK;
+    if (!leaf_values || !roots || (height && (!indices || !paths))) return ANEMOI_B200_ERR_ARG;
+    const size_t fb = felt_bytes(field);
+    if (height == 0) {
+        memcpy(roots, leaf_values, n_idx * fb);
+        return ANEMOI_B200_OK;
+    }
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    keep_pool_memory(device);
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    {
+        const size_t path_felts = n_idx * (size_t)height * (size_t)(arity - 1);
+        DevBuf d_vals, d_idx, d_paths, d_scratch, d_roots;
+        cudaError_t e = d_vals.alloc_async(n_idx * fb, st);
+        if (e == cudaSuccess) e = d_idx.alloc_async(n_idx * sizeof(uint64_t), st);
+        if (e == cudaSuccess) e = d_paths.alloc_async(path_felts * fb, st);
+        if (e == cudaSuccess) e = d_scratch.alloc_async(n_idx * (size_t)(arity + 1) * fb, st);
+        if (e == cudaSuccess) e = d_roots.alloc_async(n_idx * fb, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "device allocation");
+        if (!rc && (e = cudaMemcpyAsync(d_vals.p, leaf_values, n_idx * fb, cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = cuda_fail(e, "H2D");
+        if (!rc && (e = cudaMemcpyAsync(d_idx.p, indices, n_idx * sizeof(uint64_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = cuda_fail(e, "H2D");
+        if (!rc && (e = cudaMemcpyAsync(d_paths.p, paths, path_felts * fb, cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = cuda_fail(e, "H2D");
+        if (!rc)
+            rc = anemoi_b200_merkle_verify_dev(field, inst, arity, (const uint64_t*)d_vals.p, (const uint64_t*)d_idx.p,
+                                               (const uint64_t*)d_paths.p, height, n_idx, (uint64_t*)d_scratch.p, (uint64_t*)d_roots.p, st);
+        if (!rc && (e = cudaMemcpyAsync(roots, d_roots.p, n_idx * fb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = cuda_fail(e, "D2H");
+        e = cudaStreamSynchronize(st);
+        if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
 }
 
 }  // extern "C"

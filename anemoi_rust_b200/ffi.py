@@ -66,6 +66,12 @@ _SIGS = {
     "anemoi_b200_digest_to_bytes_dev": ([_i, _vp, _vp, _sz, _vp], _i),
     "anemoi_b200_merkle_reduce_dev": ([_i, _i, _i, _vp, _sz, _i, _vp, _vp, _vp], _i),
     "anemoi_b200_merkle_scratch_felts": ([_i, _sz], _sz),
+    "anemoi_b200_merkle_tree_felts": ([_i, _sz], _sz),
+    "anemoi_b200_merkle_tree_dev": ([_i, _i, _i, _vp, _sz, _vp, _vp], _i),
+    "anemoi_b200_merkle_open_dev": ([_i, _i, _i, _vp, _vp, _sz, _vp, _sz, _vp, _vp], _i),
+    "anemoi_b200_merkle_verify_dev": ([_i, _i, _i, _vp, _vp, _vp, _i, _sz, _vp, _vp, _vp], _i),
+    "anemoi_b200_merkle_open": ([_i, _i, _i, _vp, _sz, _vp, _sz, _vp, _vp, _i], _i),
+    "anemoi_b200_merkle_verify": ([_i, _i, _i, _vp, _vp, _vp, _i, _sz, _vp, _i], _i),
     "anemoi_b200_imad_peak": ([_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)], _i),
 }
 EXPORTED = sorted(_SIGS)

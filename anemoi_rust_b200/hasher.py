@@ -259,6 +259,55 @@ class _AnemoiBase:
                                                n_gpus))
         return out
 
+    @classmethod
+    def merkle_roots_batch(cls, leaves, leaves_per_tree):
+        """Roots of many equal-size trees stored back to back (CUDA tensor in, CUDA tensor out): one launch
+        per level over all trees at once."""
+        from . import merkle
+
+        height, m = 0, leaves_per_tree
+        while m > 1:
+            if m % cls.STATE_WIDTH:
+                raise ffi.LengthError(ffi.ERR_LENGTH, "leaves_per_tree must be a power of the arity")
+            m //= cls.STATE_WIDTH
+            height += 1
+        return merkle.merkle_reduce(cls, leaves, height)
+
+    @classmethod
+    def merkle_open(cls, leaves, indices):
+        """Build the tree over host `leaves` (n, N64) and open `indices`: returns (root (1, N64),
+        paths (n_idx, height, arity - 1, N64)). Path layout: siblings per level, leaf level first."""
+        f, ar = cls.FIELD, cls.STATE_WIDTH
+        a = _np_in(leaves, f.n64)
+        n = a.size // f.n64
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        height, m = 0, n
+        while m > 1:
+            if m % ar:
+                raise ffi.LengthError(ffi.ERR_LENGTH, "n_leaves must be a power of the arity")
+            m //= ar
+            height += 1
+        root = np.empty((1, f.n64), dtype=np.uint64)
+        paths = np.empty((idx.size, height, ar - 1, f.n64), dtype=np.uint64)
+        ffi.check(_lib.anemoi_b200_merkle_open(f.id, cls.INST, ar, _ptr(a), n, _ptr(idx), idx.size, _ptr(root),
+                                               _ptr(paths) if paths.size else None, cls.device))
+        return root, paths
+
+    @classmethod
+    def merkle_verify(cls, leaf_values, indices, paths):
+        """Recompute the root implied by each (leaf value, index, path); returns (n_idx, N64). The caller
+        compares with the committed root."""
+        f, ar = cls.FIELD, cls.STATE_WIDTH
+        v = _np_in(leaf_values, f.n64)
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        pth = np.ascontiguousarray(paths, dtype=np.uint64)
+        n_idx = idx.size
+        height = pth.size // (n_idx * (ar - 1) * f.n64) if n_idx and pth.size else 0
+        roots = np.empty((n_idx, f.n64), dtype=np.uint64)
+        ffi.check(_lib.anemoi_b200_merkle_verify(f.id, cls.INST, ar, _ptr(v), _ptr(idx), _ptr(pth) if pth.size else None,
+                                                 height, n_idx, _ptr(roots), cls.device))
+        return roots
+
     # ---- the reference's per-item API (canonical ints) ------------------------------------------
     @classmethod
     def permutation(cls, state):

@@ -144,6 +144,32 @@ int anemoi_b200_merkle_reduce_dev(int field, int inst, int arity, const uint64_t
                                   uint64_t* d_scratch, uint64_t* d_out, void* stream);
 size_t anemoi_b200_merkle_scratch_felts(int arity, size_t n_leaves);
 
+/* ---- Merkle trees with retained levels, authentication paths, batches of trees -------
+ * Not in the reference (no tree code); node function as in anemoi_b200_merkle_root. Layouts:
+ *   tree  = every level above the leaves, level 1 first (n/arity nodes), then level 2, ..., the root last:
+ *           anemoi_b200_merkle_tree_felts(arity, n_leaves) = (n_leaves - 1) / (arity - 1) elements;
+ *   path  = for one leaf index, height * (arity - 1) elements: the siblings of the queried node at each
+ *           level, leaf level first, left to right with the node's own slot skipped.
+ * A batch of equal-size trees stored back to back is reduced with anemoi_b200_merkle_reduce_dev
+ * (levels = height): it returns one root per tree. */
+size_t anemoi_b200_merkle_tree_felts(int arity, size_t n_leaves);
+/* Build the whole tree over d_leaves (n_leaves = arity^h) into d_tree; the root is its last element. */
+int anemoi_b200_merkle_tree_dev(int field, int inst, int arity, const uint64_t* d_leaves, size_t n_leaves,
+                                uint64_t* d_tree, void* stream);
+/* Openings of n_idx leaf indices (d_indices: u64, each < n_leaves) -> d_paths (n_idx paths). */
+int anemoi_b200_merkle_open_dev(int field, int inst, int arity, const uint64_t* d_leaves, const uint64_t* d_tree,
+                                size_t n_leaves, const uint64_t* d_indices, size_t n_idx, uint64_t* d_paths, void* stream);
+/* Recompute the root implied by each (leaf value, index, path): d_roots (n_idx elements). d_scratch holds
+ * n_idx * (arity + 1) elements. The caller compares the results with the committed root. */
+int anemoi_b200_merkle_verify_dev(int field, int inst, int arity, const uint64_t* d_leaf_values, const uint64_t* d_indices,
+                                  const uint64_t* d_paths, int height, size_t n_idx, uint64_t* d_scratch, uint64_t* d_roots,
+                                  void* stream);
+/* Host-pointer forms: build the tree on `device`, return the root and the openings of `indices`. */
+int anemoi_b200_merkle_open(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves,
+                            const uint64_t* indices, size_t n_idx, uint64_t* root, uint64_t* paths, int device);
+int anemoi_b200_merkle_verify(int field, int inst, int arity, const uint64_t* leaf_values, const uint64_t* indices,
+                              const uint64_t* paths, int height, size_t n_idx, uint64_t* roots, int device);
+
 /* ---- roofline denominator ------------------------------------------------------------------ */
 /* Chip-wide issue rate of one integer-multiply flavour on the current device, measured with
  * independent chains. variant: 0 mad.lo.u32, 1 mad.hi.u32, 2 mad.wide.u32, 3 carry-chained
