@@ -20,7 +20,6 @@
 
 namespace anemoi {
 
-constexpr int kBlockThreads = 128;
 
 template <int N>
 FPQ void load_felt(uint32_t (&r)[N], const uint32_t* p, int vec16) {
@@ -205,7 +204,7 @@ FPQ void chunk_to_felt(uint32_t (&r)[F::N], const uint8_t* msg, unsigned long lo
 }
 
 template <class F, int COLS>
-__global__ void __launch_bounds__(kBlockThreads, F::MIN_BLOCKS) anemoi_kernel(KernelArgs a) {
+__global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelArgs a) {
     constexpr int N = F::N;
     constexpr int W = 2 * COLS;
     extern __shared__ uint32_t smem[];

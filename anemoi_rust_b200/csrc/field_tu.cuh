@@ -12,19 +12,19 @@ template <class F, int COLS>
 static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     if (a.n == 0) return cudaSuccess;
     const unsigned long long threads = a.n * COLS;
-    // Big batches: 128-thread blocks (4 resident per SM). Small batches (upper Merkle levels, KATs): one
-    // warp per block so the few warps spread over all SMs and each gets an integer pipe to itself.
+    // Big batches: F::BLOCK-thread blocks, F::MIN_BLOCKS resident per SM. Small batches (upper Merkle levels,
+    // KATs): one warp per block so the few warps spread over all SMs.
     int device = 0, sms = 148;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int block = (threads >= (unsigned long long)sms * kBlockThreads * 2) ? kBlockThreads : 32;
+    const int block = (threads >= (unsigned long long)sms * F::BLOCK * 2) ? F::BLOCK : 32;
     const unsigned long long blocks = (threads + block - 1) / block;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     const size_t smem = (size_t)F::TABLE * F::N * sizeof(uint32_t) * block;
     static bool attr_set[64] = {};
     if (device < 64 && !attr_set[device]) {
         cudaError_t e = cudaFuncSetAttribute(anemoi_kernel<F, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)((size_t)F::TABLE * F::N * sizeof(uint32_t) * kBlockThreads));
+                                             (int)((size_t)F::TABLE * F::N * sizeof(uint32_t) * F::BLOCK));
         if (e != cudaSuccess) return e;
         attr_set[device] = true;
     }
