@@ -1,0 +1,74 @@
+"""Multi-GPU paths on real devices (skipped on a single-GPU box): the single-process
+anemoi_b200_merkle_root(..., n_gpus) and the one-process-per-GPU NCCL build of merkle.py, both against the
+1-GPU root and the oracle."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import anemoi_rust_b200 as A
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_gpus():
+    return A.device_count()
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
+def test_single_process_multi_gpu_root():
+    from oracle import c_oracle as C
+
+    for H, fi, ii, h in ((A.AnemoiPallas_4_3, 5, 1, 6), (A.AnemoiBls12_377_2_1, 0, 0, 10)):
+        f, ar = H.FIELD, H.STATE_WIDTH
+        leaves = f.random_mont(ar ** h, 11)
+        r1 = H.merkle_root(leaves, 1)
+        assert np.array_equal(r1, C.merkle_root(fi, ii, ar, leaves))
+        g = 2
+        while g <= n_gpus():
+            assert np.array_equal(H.merkle_root(leaves, g), r1), "n_gpus=%d" % g
+            g *= 2
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import anemoi_rust_b200 as A
+from anemoi_rust_b200 import merkle
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+H = A.AnemoiVesta_4_3
+f = H.FIELD
+total = 4 ** 7
+leaves = f.random_mont(total, 123)
+local = torch.from_numpy(leaves[rank * total // world:(rank + 1) * total // world].view(np.int64).copy()).cuda()
+root = merkle.merkle_root_distributed(H, local)
+torch.cuda.synchronize()
+if rank == 0:
+    full = merkle.merkle_root_device(H, torch.from_numpy(leaves.view(np.int64)).cuda())
+    assert torch.equal(root.reshape(-1), full.reshape(-1)), "sharded root != single-GPU root"
+    print("nccl-merkle-ok")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
+def test_nccl_sharded_root(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "nccl-merkle-ok" in out.stdout
