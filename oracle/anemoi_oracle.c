@@ -116,6 +116,51 @@ INL void mont_mul(uint64_t* r, const uint64_t* a, const uint64_t* b, const uint6
     for (int i = 0; i < n; i++) r[i] = t[i];
 }
 
+/* Montgomery squaring the way arkworks' square_in_place does it: upper-triangle products once, doubled,
+ * plus the diagonal, then n word-by-word Montgomery reduction rows. Same canonical result as mont_mul(a, a). */
+INL void mont_sqr(uint64_t* out, const uint64_t* a, const uint64_t* p, uint64_t n0inv, int n) {
+    uint64_t r[2 * MAXN];
+    for (int i = 0; i < 2 * n; i++) r[i] = 0;
+    for (int i = 0; i < n - 1; i++) {
+        uint64_t c = 0;
+        for (int j = i + 1; j < n; j++) {
+            u128 x = (u128)a[i] * a[j] + r[i + j] + c;
+            r[i + j] = (uint64_t)x;
+            c = (uint64_t)(x >> 64);
+        }
+        r[i + n] = c;
+    }
+    r[2 * n - 1] = r[2 * n - 2] >> 63;
+    for (int i = 2 * n - 2; i >= 2; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 63);
+    r[1] <<= 1;
+    uint64_t c = 0;
+    for (int i = 0; i < n; i++) {
+        u128 x = (u128)a[i] * a[i] + r[2 * i] + c;
+        r[2 * i] = (uint64_t)x;
+        x = (u128)r[2 * i + 1] + (uint64_t)(x >> 64);
+        r[2 * i + 1] = (uint64_t)x;
+        c = (uint64_t)(x >> 64);
+    }
+    uint64_t carry2 = 0;
+    for (int i = 0; i < n; i++) {
+        const uint64_t m = r[i] * n0inv;
+        u128 x = (u128)m * p[0] + r[i];
+        uint64_t cc = (uint64_t)(x >> 64);
+        for (int j = 1; j < n; j++) {
+            x = (u128)m * p[j] + r[i + j] + cc;
+            r[i + j] = (uint64_t)x;
+            cc = (uint64_t)(x >> 64);
+        }
+        x = (u128)r[i + n] + cc + carry2;
+        r[i + n] = (uint64_t)x;
+        carry2 = (uint64_t)(x >> 64);
+    }
+    uint64_t t[MAXN];
+    for (int i = 0; i < n; i++) t[i] = r[n + i];
+    if (carry2 || geq(t, p, n)) sub_n(t, t, p, n);
+    for (int i = 0; i < n; i++) out[i] = t[i];
+}
+
 typedef struct {
     const anemoi_field_params* f;
     int n, inst, cols, width, rate, rounds;
@@ -148,7 +193,11 @@ INL void exp_by_inv_alpha(uint64_t* r, const uint64_t* x, const ctx_t* c) {
     const int n = c->n, len = c->f->chain_len;
     uint64_t v[512][MAXN];
     for (int i = 0; i < n; i++) v[0][i] = x[i];
-    for (int s = 0; s < len; s++) mont_mul(v[s + 1], v[c->f->chain[s][0]], v[c->f->chain[s][1]], c->f->p, c->f->n0inv, n);
+    for (int s = 0; s < len; s++) {
+        const int ia = c->f->chain[s][0], ib = c->f->chain[s][1];
+        if (ia == ib) mont_sqr(v[s + 1], v[ia], c->f->p, c->f->n0inv, n); /* `.square()` steps of sbox.rs */
+        else mont_mul(v[s + 1], v[ia], v[ib], c->f->p, c->f->n0inv, n);
+    }
     for (int i = 0; i < n; i++) r[i] = v[len][i];
 }
 
@@ -191,12 +240,12 @@ INL void sbox_layer(uint64_t* s, const ctx_t* c) {
     const uint64_t* p = c->f->p;
     for (int i = 0; i < cols; i++) {
         uint64_t *x = s + i * n, *y = s + (cols + i) * n, y2[MAXN], g[MAXN], t[MAXN];
-        mont_mul(y2, y, y, p, c->f->n0inv, n);
+        mont_sqr(y2, y, p, c->f->n0inv, n);
         mul_by_generator(g, y2, c);
         sub_mod(x, x, g, p, n);
         exp_by_inv_alpha(t, x, c);
         sub_mod(y, y, t, p, n);
-        mont_mul(y2, y, y, p, c->f->n0inv, n);
+        mont_sqr(y2, y, p, c->f->n0inv, n);
         mul_by_generator(g, y2, c);
         add_mod(x, x, g, p, n);
         add_mod(x, x, c->f->delta, p, n);
