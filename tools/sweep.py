@@ -145,6 +145,40 @@ def cfg5(out, sizes, only):
             torch.cuda.empty_cache()
 
 
+def readme_shapes(out):
+    """The four shapes the reference's README publishes single-thread CPU latencies for (README.md:77-85):
+    2->1 Jive compress and `hash` of a 10 KB byte string, on BLS12-377 and Vesta, Anemoi-2-1 and 4-3."""
+    published_us = {("bls12_377", "anemoi_2_1"): (429.61, 85369.0), ("bls12_377", "anemoi_4_3"): (485.99, 35937.0),
+                    ("vesta", "anemoi_2_1"): (129.48, 44448.0), ("vesta", "anemoi_4_3"): (176.58, 20307.0)}
+    for (field, inst), (c_us, h_us) in published_us.items():
+        H = A.HASHERS[(field, inst)]
+        f, W = H.FIELD, H.STATE_WIDTH
+        fi, ii = ids(field, inst)
+        n = 1 << 20
+        x = device_random(f, n * W, 0xA7E301 + 77)
+        o = torch.empty((n * (W // 2), f.n64), dtype=torch.int64, device=dev)
+        ms_c = timed(lambda: H.compress_batch(x, out=o), reps=2)
+        # two full waves of resident threads: 148 SMs x (512 | 768 threads) x 2 / threads-per-message
+        nm, nb = 2 * 148 * (512 if f.n64 == 6 else 768) // H.NUM_COLUMNS, 10240
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        data = torch.randint(0, 256, (nm, nb), dtype=torch.uint8, device=dev, generator=g)
+        dig = torch.empty((nm, f.n64), dtype=torch.int64, device=dev)
+
+        def run_hash():
+            ffi.check(ffi.lib.anemoi_b200_hash_bytes_dev(f.id, H.INST, ctypes.c_void_p(data.data_ptr()), nm, nb,
+                                                        ctypes.c_void_p(dig.data_ptr()), None))
+
+        ms_h = timed(run_hash)
+        sample = data[:8].cpu().numpy()
+        ok = bool(np.array_equal(dig[:8].cpu().numpy().view(np.uint64), C.hash_bytes(fi, ii, sample, 8, nb)))
+        emit({"config": "readme", "field": field, "inst": inst,
+              "compress_2to1_per_s": n / ms_c * 1e3, "reference_published_compress_us_1thread": c_us,
+              "speedup_vs_published_1thread_compress": (n / ms_c * 1e3) * c_us * 1e-6,
+              "hash_10KB_messages_per_s": nm / ms_h * 1e3, "reference_published_hash10KB_us_1thread": h_us,
+              "speedup_vs_published_1thread_hash": (nm / ms_h * 1e3) * h_us * 1e-6, "oracle_sample_ok": ok}, out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="2,3,4,5")
@@ -153,7 +187,9 @@ def main():
     ap.add_argument("--cfg2-log2", type=int, default=18)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    cfgs = [int(c) for c in args.configs.split(",")]
+    cfgs = [int(c) for c in args.configs.split(",") if c != "readme"]
+    if "readme" in args.configs.split(","):
+        readme_shapes(args.out)
     emit({"gpu": torch.cuda.get_device_name(0), "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
           "peak_TMAC32": PEAK * 1e-12}, args.out)
     if 2 in cfgs:
