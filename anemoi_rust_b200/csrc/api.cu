@@ -494,6 +494,42 @@ int anemoi_b200_compress(int field, int inst, int k, const uint64_t* in, uint64_
     });
 }
 
+int anemoi_b200_compress_multi(int field, int inst, int k, const uint64_t* in, uint64_t* out, size_t n, int n_gpus) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    int per = 0;
+    int mode = jive_mode(inst, k, &per);
+    if (mode < 0) return mode;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!in || !out) return ANEMOI_B200_ERR_ARG;
+    const int count = anemoi_b200_device_count();
+    if (count == 0) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "no CUDA device");
+        return ANEMOI_B200_ERR_NO_DEVICE;
+    }
+    if (n_gpus < 1 || n_gpus > count) return ANEMOI_B200_ERR_ARG;
+    if ((size_t)n_gpus > n) n_gpus = (int)n;
+    if (n_gpus == 1) return anemoi_b200_compress(field, inst, k, in, out, n, 0);
+    const size_t in_words = (size_t)width_of(inst) * kFieldLimbs[field], out_words = (size_t)per * kFieldLimbs[field];
+    std::vector<int> rcs(n_gpus, ANEMOI_B200_OK);
+    std::vector<std::string> errs(n_gpus);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_gpus; g++) {
+        const size_t lo = n * (size_t)g / (size_t)n_gpus, hi = n * (size_t)(g + 1) / (size_t)n_gpus;
+        th.emplace_back([&, g, lo, hi]() {
+            rcs[g] = anemoi_b200_compress(field, inst, k, in + lo * in_words, out + lo * out_words, hi - lo, g);
+            errs[g] = g_cuda_err;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < n_gpus; g++)
+        if (rcs[g]) {
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "gpu %d: %s", g, errs[g].c_str());
+            return rcs[g];
+        }
+    return ANEMOI_B200_OK;
+}
+
 int anemoi_b200_hash_field(int field, int inst, const uint64_t* elems, size_t n_msgs, size_t felts_per_msg,
                            uint64_t* digests, int device) {
     int rc = check_fi(field, inst);

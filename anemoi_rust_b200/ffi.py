@@ -50,6 +50,7 @@ _SIGS = {
     "anemoi_b200_permute": ([_i, _i, _vp, _sz, _i], _i),
     "anemoi_b200_sbox_layer": ([_i, _i, _vp, _sz, _i], _i),
     "anemoi_b200_compress": ([_i, _i, _i, _vp, _vp, _sz, _i], _i),
+    "anemoi_b200_compress_multi": ([_i, _i, _i, _vp, _vp, _sz, _i], _i),
     "anemoi_b200_hash_field": ([_i, _i, _vp, _sz, _sz, _vp, _i], _i),
     "anemoi_b200_hash_field_ragged": ([_i, _i, _vp, _vp, _sz, _vp, _i], _i),
     "anemoi_b200_hash_bytes": ([_i, _i, _vp, _sz, _sz, _vp, _i], _i),

@@ -146,8 +146,9 @@ class _AnemoiBase:
         return a
 
     @classmethod
-    def compress_k_batch(cls, states, k, out=None):
-        """Jive::compress_k on n states: (n*W felts) -> (n*W/k felts)."""
+    def compress_k_batch(cls, states, k, out=None, n_gpus=1):
+        """Jive::compress_k on n states: (n*W felts) -> (n*W/k felts). n_gpus > 1 (host arrays only) splits the
+        batch over that many devices of this process; independent states need no collective."""
         f, W = cls.FIELD, cls.STATE_WIDTH
         if k <= 0 or W % k or k % 2:
             raise ffi.ArityError(ffi.ERR_ARITY, "compress_k: k must be even and divide STATE_WIDTH")
@@ -170,7 +171,10 @@ class _AnemoiBase:
         n = a.size // (W * f.n64)
         if out is None:
             out = np.empty((n * per, f.n64), dtype=np.uint64)
-        ffi.check(_lib.anemoi_b200_compress(f.id, cls.INST, k, _ptr(a), _ptr(out), n, cls.device))
+        if n_gpus > 1:
+            ffi.check(_lib.anemoi_b200_compress_multi(f.id, cls.INST, k, _ptr(a), _ptr(out), n, n_gpus))
+        else:
+            ffi.check(_lib.anemoi_b200_compress(f.id, cls.INST, k, _ptr(a), _ptr(out), n, cls.device))
         return out
 
     @classmethod

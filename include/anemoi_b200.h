@@ -85,6 +85,10 @@ int anemoi_b200_sbox_layer(int field, int inst, uint64_t* states, size_t n, int 
  * k = 2 is Jive::compress. Any other k -> ERR_ARITY (the reference panics). */
 int anemoi_b200_compress(int field, int inst, int k, const uint64_t* in, uint64_t* out, size_t n, int device);
 
+/* Same, with the batch split into n_gpus contiguous slices, one per device 0..n_gpus-1, processed concurrently
+ * (one host thread + stream per device; independent states need no collective). */
+int anemoi_b200_compress_multi(int field, int inst, int k, const uint64_t* in, uint64_t* out, size_t n, int n_gpus);
+
 /* Sponge::hash_field (2-1: src/<field>/anemoi_2_1/hasher.rs:68-85; 4-3: anemoi_4_3/hasher.rs:93-129)
  * on n_msgs messages of felts_per_msg elements each (message i at elems[i*felts_per_msg ...]).
  * digests = n_msgs elements. felts_per_msg may be 0. */

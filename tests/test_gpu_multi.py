@@ -34,6 +34,18 @@ def test_single_process_multi_gpu_root():
             g *= 2
 
 
+@pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
+def test_single_process_multi_gpu_compress():
+    H = A.AnemoiBn254_4_3
+    f = H.FIELD
+    x = f.random_mont(4 * 3001, 21)   # odd count: uneven slices
+    one = H.compress_k_batch(x, 4)
+    g = 2
+    while g <= n_gpus():
+        assert np.array_equal(H.compress_k_batch(x, 4, n_gpus=g), one)
+        g *= 2
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)
