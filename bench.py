@@ -297,11 +297,20 @@ def main():
         f4 = H4.FIELD
         total = 4 ** args.merkle_log4
         local = total // world
-        g = torch.Generator(device=dev)
-        g.manual_seed(SEED + 3 + rank)
-        # p = 2^254 + t: every value below 2^254 is canonical, so mask the top limb to 62 bits
-        leaves = torch.randint(-(1 << 63), (1 << 63) - 1, (local, f4.n64), dtype=torch.int64, device=dev, generator=g)
-        leaves[:, f4.n64 - 1] &= (1 << 62) - 1
+        # the leaf array is 8 fixed, individually seeded chunks; rank r of N takes chunks [8r/N, 8(r+1)/N), so the
+        # tree -- and therefore root_limb0 -- is the same for N = 1, 2, 4, 8 (end-to-end check of the sharded build)
+        chunks = 8 if (world in (1, 2, 4, 8) and total % 8 == 0) else world
+        per_chunk = total // chunks
+        parts = []
+        for c in range(rank * chunks // world, (rank + 1) * chunks // world):
+            g = torch.Generator(device=dev)
+            g.manual_seed(SEED + 3 + c)
+            # p = 2^254 + t: every value below 2^254 is canonical, so mask the top limb to 62 bits
+            part = torch.randint(-(1 << 63), (1 << 63) - 1, (per_chunk, f4.n64), dtype=torch.int64, device=dev, generator=g)
+            part[:, f4.n64 - 1] &= (1 << 62) - 1
+            parts.append(part)
+        leaves = torch.cat(parts) if len(parts) > 1 else parts[0]
+        del parts
         scratch = torch.empty((ffi.lib.anemoi_b200_merkle_scratch_felts(4, local), f4.n64), dtype=torch.int64, device=dev)
         root = merkle.merkle_root_distributed(H4, leaves, scratch=scratch)  # warm-up (also NCCL)
         barrier()
