@@ -58,7 +58,7 @@ FPQ void store_felt(uint32_t* p, const uint32_t (&r)[N], int vec16) {
 template <class F>
 FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
     constexpr int N = F::N;
-    constexpr bool CANON = F::SPARE_BITS < 2;  // >= 2 spare bits: stay in [0, 2p) between multiplies
+    constexpr bool CANON = !F::LAZY;  // lazy fields stay in [0, 2p + small) between multiplies (generated/fields.cuh)
     {
         uint32_t x2[N], t[N];
         fp::mont_sqr<F, CANON>(x2, x);
@@ -90,7 +90,10 @@ FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t*
             fp::mont_mul<F, CANON>(acc, acc, b);
         }
     }
-    if (!CANON) fp::cond_sub_p<F>(acc);
+    if (!CANON) {
+        fp::cond_sub_p<F>(acc);
+        if (F::FINAL_SUBS == 2) fp::cond_sub_p<F>(acc);
+    }
 #pragma unroll
     for (int l = 0; l < N; l++) r[l] = acc[l];
 }
