@@ -314,7 +314,7 @@ FPQ void mad_redc_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t
         cmad_row<N>(even, a, bi);
         addc(odd[N - 1], 0u);
     }
-    uint32_t m = mul_lo(even[0], F::n0inv());
+    uint32_t m = F::quotient_digit(even[0]);
     ModRow<F>::cmad_odd(odd, m);
     ModRow<F>::cmad_even(even, m);
     addc(odd[N - 1], 0u);
@@ -353,13 +353,13 @@ template <class F>
 FPQ void redc_row(uint32_t* even, uint32_t* odd, bool first) {
     constexpr int N = F::N;
     if (first) {
-        uint32_t m = mul_lo(even[0], F::n0inv());
+        uint32_t m = F::quotient_digit(even[0]);
         ModRow<F>::mul_odd(odd, m);
         ModRow<F>::cmad_even(even, m);
         addc(odd[N - 1], 0u);
     } else {
         add_cc(even[0], odd[1]);
-        uint32_t m = mul_lo(even[0], F::n0inv());  // mul.lo does not touch the carry flag
+        uint32_t m = F::quotient_digit(even[0]);  // mul.lo does not touch the carry flag
         ModRow<F>::madc_odd_rshift(odd, m);
         ModRow<F>::cmad_even(even, m);
         addc(odd[N - 1], 0u);
