@@ -258,9 +258,14 @@ __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelA
             const unsigned long long o0 = a.offsets[unit], o1 = a.offsets[unit + 1];
             msg_len = o1 - o0;
             msg_felts = a.in + o0 * N;
-        } else {  // MODE_HASH_BYTES
+        } else if (mode == MODE_HASH_BYTES) {
             msg_nbytes = a.len;
             msg_bytes = reinterpret_cast<const uint8_t*>(a.in) + unit * a.len;
+            msg_len = (msg_nbytes + F::BYTE_CHUNK - 1) / F::BYTE_CHUNK;
+        } else {  // MODE_HASH_BYTES_RAGGED
+            const unsigned long long o0 = a.offsets[unit], o1 = a.offsets[unit + 1];
+            msg_nbytes = o1 - o0;
+            msg_bytes = reinterpret_cast<const uint8_t*>(a.in) + o0;
             msg_len = (msg_nbytes + F::BYTE_CHUNK - 1) / F::BYTE_CHUNK;
         }
         // 2-1: one permutation per element, no padding (hasher.rs:68-85).
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelA
 
 #pragma unroll 1
     for (unsigned long long it = 0; it < nperm; it++) {
-        if (mode >= MODE_HASH && mode <= MODE_HASH_BYTES) {
+        if ((mode >= MODE_HASH && mode <= MODE_HASH_BYTES) || mode == MODE_HASH_BYTES_RAGGED) {
             // absorb: slot s of the rate <- element RATE*it + s; the slot just past the end gets the
             // padding 1 (4-3 only; it exists only when len % 3 != 0, i.e. sigma == 0).
             // 2-1 slots: {x}. 4-3 slots: s=0 -> col0.x, s=1 -> col1.x, s=2 -> col0.y.
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelA
                 uint32_t e[N];
                 bool have = false;
                 if (idx < msg_len) {
-                    if (mode == MODE_HASH_BYTES) chunk_to_felt<F>(e, msg_bytes, msg_nbytes, idx);
+                    if (mode == MODE_HASH_BYTES || mode == MODE_HASH_BYTES_RAGGED) chunk_to_felt<F>(e, msg_bytes, msg_nbytes, idx);
                     else load_felt<N>(e, msg_felts + idx * N, a.vec16);
                     have = true;
                 } else if (COLS == 2 && idx == msg_len) {

@@ -67,7 +67,8 @@ int launch(int field, int inst, int mode, const void* in, void* out, const uint6
     a.mode = mode;
     // felts are 32 or 48 bytes, so a 16-byte-aligned base keeps every felt 16-byte aligned
     a.vec16 = aligned16(in, out);
-    if (mode == anemoi::MODE_HASH_BYTES) a.vec16 = aligned16(out, out);  // the byte input is read bytewise
+    if (mode == anemoi::MODE_HASH_BYTES || mode == anemoi::MODE_HASH_BYTES_RAGGED)
+        a.vec16 = aligned16(out, out);  // the byte input is read bytewise
     const int cols = (mode == anemoi::MODE_TO_BYTES) ? 1 : (inst == ANEMOI_INST_2_1 ? 1 : 2);
     cudaError_t e = kLaunch[field](cols, &a, stream);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
@@ -304,6 +305,15 @@ int anemoi_b200_hash_bytes_dev(int field, int inst, const uint8_t* d_bytes, size
     if (!d_digests || (!d_bytes && bytes_per_msg)) return ANEMOI_B200_ERR_ARG;
     return launch(field, inst, anemoi::MODE_HASH_BYTES, d_bytes, d_digests, nullptr, n_msgs, bytes_per_msg,
                   (cudaStream_t)stream);
+}
+
+int anemoi_b200_hash_bytes_ragged_dev(int field, int inst, const uint8_t* d_bytes, const uint64_t* d_offsets,
+                                      size_t n_msgs, uint64_t* d_digests, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!d_digests || !d_offsets) return ANEMOI_B200_ERR_ARG;
+    return launch(field, inst, anemoi::MODE_HASH_BYTES_RAGGED, d_bytes, d_digests, d_offsets, n_msgs, 0, (cudaStream_t)stream);
 }
 
 int anemoi_b200_merge_dev(int field, int inst, const uint64_t* d_pairs, uint64_t* d_out, size_t n, void* stream) {
@@ -583,6 +593,30 @@ int anemoi_b200_hash_bytes(int field, int inst, const uint8_t* bytes, size_t n_m
                          return anemoi_b200_hash_bytes_dev(field, inst, (const uint8_t*)di, n_msgs, bytes_per_msg,
                                                            (uint64_t*)dout, st);
                      });
+}
+
+int anemoi_b200_hash_bytes_ragged(int field, int inst, const uint8_t* bytes, const uint64_t* offsets, size_t n_msgs,
+                                  uint64_t* digests, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (n_msgs == 0) return ANEMOI_B200_OK;
+    if (!digests || !offsets) return ANEMOI_B200_ERR_ARG;
+    for (size_t i = 0; i < n_msgs; i++)
+        if (offsets[i + 1] < offsets[i]) return ANEMOI_B200_ERR_LENGTH;
+    const uint64_t base = offsets[0], total = offsets[n_msgs] - base;
+    if (total && !bytes) return ANEMOI_B200_ERR_ARG;
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    std::vector<uint64_t> rel(n_msgs + 1);
+    for (size_t i = 0; i <= n_msgs; i++) rel[i] = offsets[i] - base;
+    DevBuf d_off;
+    CK(d_off.alloc((n_msgs + 1) * sizeof(uint64_t)));
+    CK(cudaMemcpy(d_off.p, rel.data(), (n_msgs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    const void* src = total ? (const void*)(bytes + base) : (const void*)rel.data();
+    return host_call(device, src, total, digests, n_msgs * felt_bytes(field), false, [&](void* di, void* dout, cudaStream_t st) {
+        return anemoi_b200_hash_bytes_ragged_dev(field, inst, (const uint8_t*)di, (const uint64_t*)d_off.p, n_msgs,
+                                                 (uint64_t*)dout, st);
+    });
 }
 
 int anemoi_b200_merge(int field, int inst, const uint64_t* digest_pairs, uint64_t* out, size_t n, int device) {

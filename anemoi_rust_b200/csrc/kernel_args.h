@@ -14,12 +14,13 @@ enum Mode : int {
     MODE_HASH_BYTES = 6,   // sponge hash (bytes), fixed length per message
     MODE_MERGE43 = 7,      // 4-3 sponge merge: [d0, d0, 0, 0] (sic, reference ignores d1)
     MODE_TO_BYTES = 8,     // digest.to_bytes: de-Montgomery, one felt per unit (no permutation)
+    MODE_HASH_BYTES_RAGGED = 9,  // sponge hash (bytes), byte offsets[]
 };
 
 struct KernelArgs {
     const uint32_t* in;
     uint32_t* out;
-    const unsigned long long* offsets;  // MODE_HASH_RAGGED: n + 1 element offsets
+    const unsigned long long* offsets;  // MODE_HASH_RAGGED: n + 1 element offsets; MODE_HASH_BYTES_RAGGED: byte offsets
     unsigned long long n;               // states / messages / felts
     unsigned long long len;             // felts (MODE_HASH) or bytes (MODE_HASH_BYTES) per message
     int mode;

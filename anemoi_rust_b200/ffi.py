@@ -54,6 +54,8 @@ _SIGS = {
     "anemoi_b200_hash_field": ([_i, _i, _vp, _sz, _sz, _vp, _i], _i),
     "anemoi_b200_hash_field_ragged": ([_i, _i, _vp, _vp, _sz, _vp, _i], _i),
     "anemoi_b200_hash_bytes": ([_i, _i, _vp, _sz, _sz, _vp, _i], _i),
+    "anemoi_b200_hash_bytes_ragged": ([_i, _i, _vp, _vp, _sz, _vp, _i], _i),
+    "anemoi_b200_hash_bytes_ragged_dev": ([_i, _i, _vp, _vp, _sz, _vp, _vp], _i),
     "anemoi_b200_merge": ([_i, _i, _vp, _vp, _sz, _i], _i),
     "anemoi_b200_merkle_root": ([_i, _i, _i, _vp, _sz, _vp, _i], _i),
     "anemoi_b200_digest_to_bytes": ([_i, _vp, _vp, _sz, _i], _i),

@@ -242,6 +242,20 @@ class _AnemoiBase:
         return out
 
     @classmethod
+    def hash_ragged(cls, messages):
+        """Sponge::hash on a list of byte strings of different lengths (one kernel launch)."""
+        f = cls.FIELD
+        lens = np.array([len(m) for m in messages], dtype=np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        blob = np.frombuffer(b"".join(bytes(m) for m in messages), dtype=np.uint8)
+        if blob.size == 0:
+            blob = np.zeros(1, dtype=np.uint8)
+        out = np.empty((len(messages), f.n64), dtype=np.uint64)
+        ffi.check(_lib.anemoi_b200_hash_bytes_ragged(f.id, cls.INST, _ptr(np.ascontiguousarray(blob)), _ptr(offs),
+                                                     len(messages), _ptr(out), cls.device))
+        return out
+
+    @classmethod
     def merge_batch(cls, digest_pairs):
         """Sponge::merge on n pairs: (n, 2, N64) -> (n, N64)."""
         f = cls.FIELD

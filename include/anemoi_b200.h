@@ -106,6 +106,10 @@ int anemoi_b200_hash_field_ragged(int field, int inst, const uint64_t* elems, co
 int anemoi_b200_hash_bytes(int field, int inst, const uint8_t* bytes, size_t n_msgs, size_t bytes_per_msg,
                            uint64_t* digests, int device);
 
+/* Ragged form of anemoi_b200_hash_bytes: message i is bytes[offsets[i] .. offsets[i+1]) (n_msgs + 1 byte offsets). */
+int anemoi_b200_hash_bytes_ragged(int field, int inst, const uint8_t* bytes, const uint64_t* offsets, size_t n_msgs,
+                                  uint64_t* digests, int device);
+
 /* Sponge::merge on n digest pairs (in = 2n elements, out = n elements).
  *   2-1: Jive compress (anemoi_2_1/hasher.rs:87-92).
  *   4-3: the reference's sponge merge, which copies digests[0] twice and never reads digests[1]
@@ -135,6 +139,8 @@ int anemoi_b200_hash_field_ragged_dev(int field, int inst, const uint64_t* d_ele
                                       size_t n_msgs, uint64_t* d_digests, void* stream);
 int anemoi_b200_hash_bytes_dev(int field, int inst, const uint8_t* d_bytes, size_t n_msgs, size_t bytes_per_msg,
                                uint64_t* d_digests, void* stream);
+int anemoi_b200_hash_bytes_ragged_dev(int field, int inst, const uint8_t* d_bytes, const uint64_t* d_offsets,
+                                      size_t n_msgs, uint64_t* d_digests, void* stream);
 int anemoi_b200_merge_dev(int field, int inst, const uint64_t* d_pairs, uint64_t* d_out, size_t n, void* stream);
 int anemoi_b200_digest_to_bytes_dev(int field, const uint64_t* d_digests, uint8_t* d_bytes, size_t n, void* stream);
 

@@ -101,6 +101,28 @@ struct Anemoi {
         return root;
     }
 
+    // Openings (authentication paths) of `indices` in the tree over `leaves`; returns the root, fills `paths`
+    // with indices.size() * height * (STATE_WIDTH - 1) elements (siblings per level, leaf level first).
+    static F merkle_open(const std::vector<F>& leaves, const std::vector<uint64_t>& indices, std::vector<F>& paths,
+                         int device = 0) {
+        int height = 0;
+        for (size_t m = leaves.size(); m > 1; m /= STATE_WIDTH) height++;
+        paths.assign(indices.size() * (size_t)height * (STATE_WIDTH - 1), F{});
+        F root{};
+        check(anemoi_b200_merkle_open(FIELD, INST, STATE_WIDTH, raw(leaves.data()), leaves.size(), indices.data(),
+                                      indices.size(), raw(&root), paths.empty() ? nullptr : raw(paths.data()), device));
+        return root;
+    }
+    // Roots implied by (leaf value, index, path) triples; compare with the committed root.
+    static std::vector<F> merkle_verify(const std::vector<F>& leaf_values, const std::vector<uint64_t>& indices,
+                                        const std::vector<F>& paths, int height, int device = 0) {
+        std::vector<F> roots(indices.size());
+        check(anemoi_b200_merkle_verify(FIELD, INST, STATE_WIDTH, raw(leaf_values.data()), indices.data(),
+                                        paths.empty() ? nullptr : raw(paths.data()), height, indices.size(),
+                                        raw(roots.data()), device));
+        return roots;
+    }
+
     // ---- the reference's per-item API ----------------------------------------------------------
     // Anemoi::permutation(&mut [F]) -- src/traits.rs:370
     static void permutation(std::vector<F>& state) {

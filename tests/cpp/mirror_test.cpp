@@ -42,6 +42,13 @@ int main() {
     auto l1 = H4::compress_k_batch(leaves, 4);
     auto root2 = H4::compress_k(l1, 4);
     if (root != root2[0]) { printf("FAIL: merkle_root != iterated compress_k\n"); return 1; }
+    std::vector<H4::F> paths;
+    std::vector<uint64_t> idx = {0, 7, 15};
+    auto root3 = H4::merkle_open(leaves, idx, paths);
+    if (root3 != root || paths.size() != 3 * 2 * 3) { printf("FAIL: merkle_open\n"); return 1; }
+    std::vector<H4::F> vals = {leaves[0], leaves[7], leaves[15]};
+    auto roots = H4::merkle_verify(vals, idx, paths, 2);
+    for (auto& r : roots) if (r != root) { printf("FAIL: merkle_verify\n"); return 1; }
     printf("OK\n");
     return 0;
 }

@@ -66,6 +66,10 @@ def test_sponge_random(field, inst):
         data = rng.integers(0, 256, size=(n, nb), dtype=np.uint8)
         got = H.hash_batch(data, bytes_per_msg=nb) if nb else H.hash_batch(np.zeros((n, 0), dtype=np.uint8))
         assert np.array_equal(got, C.hash_bytes(fi, ii, data, n, nb))
+    # ragged byte strings in one launch
+    msgs = [bytes(rng.integers(0, 256, size=int(L), dtype=np.uint8)) for L in (0, 1, B, B + 1, 5 * B, 7, 3 * B - 1, 0, 1000)]
+    exp = np.concatenate([C.hash_bytes(fi, ii, np.frombuffer(m, dtype=np.uint8), 1, len(m)) for m in msgs])
+    assert np.array_equal(H.hash_ragged(msgs), exp)
     # merge + digest bytes
     d = f.random_mont(2 * 37, SEED + 30)
     assert np.array_equal(H.merge_batch(d), C.merge(fi, ii, d))
