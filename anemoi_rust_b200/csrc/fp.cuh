@@ -68,9 +68,6 @@ FPQ void madc_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { emu_mad
 FPQ void madc_wide_cc_to(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
     emu_mad_pair(dlo, dhi, a, b, clo, chi, true, true);
 }
-FPQ void mad_wide_cc_to(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
-    emu_mad_pair(dlo, dhi, a, b, clo, chi, false, true);
-}
 FPQ void add_cc(uint32_t& a, uint32_t b) { uint64_t t = (uint64_t)a + b; a = (uint32_t)t; g_cc = (uint32_t)(t >> 32); }
 FPQ void addc_cc(uint32_t& a, uint32_t b) { uint64_t t = (uint64_t)a + b + g_cc; a = (uint32_t)t; g_cc = (uint32_t)(t >> 32); }
 FPQ void addc(uint32_t& a, uint32_t b) { a = a + b + g_cc; }
@@ -99,11 +96,6 @@ FPQ void madc_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
 // {dlo,dhi} = a*b + {clo,chi} + carry ; carry out
 FPQ void madc_wide_cc_to(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
-                 : "=r"(dlo), "=r"(dhi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
-}
-// {dlo,dhi} = a*b + {clo,chi} ; carry out
-FPQ void mad_wide_cc_to(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
-    asm volatile("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
                  : "=r"(dlo), "=r"(dhi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
 }
 FPQ void add_cc(uint32_t& a, uint32_t b) { asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a) : "r"(b)); }
