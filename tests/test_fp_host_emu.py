@@ -66,3 +66,43 @@ def test_fp_ops(emu, field):
             r = call(emu, fi, 3, n, a)
             assert r % p == a * a * Rinv % p
             assert r < (2 * p + 2 * drift + (1 << 128) if near_lazy else 2 * p)
+
+
+def adversarial_values(p, n, rng, count=200):
+    """Operands whose limbs are drawn from {0, 1, 0x7fffffff, 0x80000000, 0xfffffffe, 0xffffffff, random}:
+    long carry/borrow ripples and all-ones products that uniform sampling never hits."""
+    special = [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF]
+    out = []
+    while len(out) < count:
+        limbs = [rng.choice(special) if rng.random() < 0.8 else rng.getrandbits(32) for _ in range(n)]
+        v = sum(l << (32 * i) for i, l in enumerate(limbs))
+        out.append(v % p)
+        out.append((v >> rng.randrange(0, 64)) % p)
+    return out
+
+
+@pytest.mark.parametrize("field", R.FIELDS)
+def test_fp_adversarial_limbs(emu, field):
+    P = R.params(field, "anemoi_2_1")
+    fi = R.FIELDS.index(field)
+    n = emu.fp_emu_limbs(fi)
+    p = P.p
+    Rinv = pow(1 << (32 * n), -1, p)
+    rng = random.Random(4242 + fi)
+    vals = adversarial_values(p, n, rng)
+    for i, a in enumerate(vals):
+        b = vals[(7 * i + 3) % len(vals)]
+        assert call(emu, fi, 0, n, a, b) == a * b * Rinv % p
+        assert call(emu, fi, 1, n, a) == a * a * Rinv % p
+        assert call(emu, fi, 4, n, a, b) == (a + b) % p
+        assert call(emu, fi, 5, n, a, b) == (a - b) % p
+    spare = 32 * n - p.bit_length()
+    near_lazy = spare < 2 and 0 <= 4 * p - (1 << (32 * n)) < (1 << 130)
+    if spare >= 2 or near_lazy:
+        hi = 2 * p + ((1 << 140) if near_lazy else 0)
+        lazy = [v + rng.choice([0, p, hi - p - 1]) for v in vals]
+        lazy = [v if v < hi else v - p for v in lazy]
+        for i, a in enumerate(lazy):
+            b = lazy[(5 * i + 1) % len(lazy)]
+            assert call(emu, fi, 2, n, a, b) % p == a * b * Rinv % p
+            assert call(emu, fi, 3, n, a) % p == a * a * Rinv % p

@@ -179,3 +179,27 @@ def test_full_size_config1_properties():
     root = H.merkle_root(leaves)
     sub = np.concatenate([H.merkle_root(c) for c in leaves.reshape(64, -1, f.n64)])
     assert np.array_equal(H.merkle_root(sub), root)
+
+
+@pytest.mark.parametrize("field,inst", CASES)
+def test_adversarial_limb_patterns(field, inst):
+    """States whose Montgomery limbs are all-ones / zero / sign-bit patterns (reduced mod p): long carry and
+    borrow ripples that uniform inputs never produce. Compress and permute vs the oracle."""
+    import random
+
+    H = HASHERS[(field, inst)]
+    fi, ii = ids(field, inst)
+    f, W = H.FIELD, H.STATE_WIDTH
+    rng = random.Random(99)
+    special = [0, 1, 0x7FFFFFFFFFFFFFFF, 0x8000000000000000, 0xFFFFFFFFFFFFFFFE, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF00000000,
+               0x00000000FFFFFFFF]
+    vals = []
+    for _ in range(W * 257):
+        limbs = [rng.choice(special) if rng.random() < 0.8 else rng.getrandbits(64) for _ in range(f.n64)]
+        v = sum(l << (64 * i) for i, l in enumerate(limbs)) % f.p
+        vals.append(v)
+    vals[:W] = [f.p - 1] * W
+    vals[W:2 * W] = [0] * W
+    x = np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(f.n64)] for v in vals], dtype=np.uint64)
+    assert np.array_equal(H.permutation_batch(x), C.permute(fi, ii, x))
+    assert np.array_equal(H.compress_k_batch(x, W), C.compress(fi, ii, W, x))
