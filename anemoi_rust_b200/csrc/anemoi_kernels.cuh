@@ -53,12 +53,17 @@ FPQ void store_felt(uint32_t* p, const uint32_t (&r)[N], int vec16) {
     }
 }
 
-// x^INV_ALPHA -- replaces sbox::exp_by_inv_alpha (src/<field>/sbox.rs). tbl points at this thread's
-// column of the shared-memory table: entry k, limb l at tbl[(k*N + l) * stride].
+// x^INV_ALPHA -- replaces sbox::exp_by_inv_alpha (src/<field>/sbox.rs). Any addition chain yields the same
+// canonical residue as the reference's hard-coded one, so each field runs the cheapest ladder whose live set fits
+// in shared memory (tools/gen_params.py). tbl points at this thread's column of the shared-memory slots:
+// slot k, limb l at tbl[(k*N + l) * stride].
+//
+// (1) Sliding-window ladder (w = 4): slots hold the odd powers x, x^3, .., x^15; the schedule {squarings, slot}
+//     comes from constant memory (warp-uniform, no divergence).
 template <class F>
-FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
+FPQ void pow_window(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
     constexpr int N = F::N;
-    constexpr bool CANON = !F::LAZY;  // lazy fields stay in [0, 2p + small) between multiplies (generated/fields.cuh)
+    constexpr bool CANON = !F::LAZY;
     {
         uint32_t x2[N], t[N];
         fp::mont_sqr<F, CANON>(x2, x);
@@ -68,19 +73,19 @@ FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t*
             tbl[l * stride] = x[l];
         }
 #pragma unroll 1
-        for (int k = 1; k < F::TABLE; k++) {
+        for (int k = 1; k < F::SLOTS; k++) {
             fp::mont_mul<F, CANON>(t, t, x2);
 #pragma unroll
             for (int l = 0; l < N; l++) tbl[(k * N + l) * stride] = t[l];
         }
     }
-    uint32_t acc[N];
 #pragma unroll
     for (int l = 0; l < N; l++) acc[l] = tbl[(F::SCHED_FIRST * N + l) * stride];
+    const uint8_t* sched = Tables<F>::prog();
 #pragma unroll 1
     for (int s = 0; s < F::SCHED_LEN; s++) {
-        const int nsq = Tables<F>::sched()[2 * s];
-        const int idx = Tables<F>::sched()[2 * s + 1];
+        const int nsq = sched[2 * s];
+        const int idx = sched[2 * s + 1];
 #pragma unroll 1
         for (int q = 0; q < nsq; q++) fp::mont_sqr<F, CANON>(acc, acc);
         if (idx != 255) {
@@ -90,7 +95,50 @@ FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t*
             fp::mont_mul<F, CANON>(acc, acc, b);
         }
     }
-    if (!CANON) {
+}
+
+// (2) Accumulator machine running the reference crate's own addition chain, compiled onto slots by
+//     tools/gen_params.py (Pallas: 252 S + 43 M in 11 slots, Vesta: 248 S + 45 M in 12 slots, against 250 S + 56 M
+//     for the best window ladder): SQR n, MUL slot, LD slot, ST slot; slot 0 = x.
+template <class F>
+FPQ void pow_program(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
+    constexpr int N = F::N;
+    constexpr bool CANON = !F::LAZY;
+#pragma unroll
+    for (int l = 0; l < N; l++) {
+        acc[l] = x[l];
+        tbl[l * stride] = x[l];
+    }
+    const uint8_t* prog = Tables<F>::prog();
+#pragma unroll 1
+    for (int pc = 0; pc < F::PROG_LEN; pc++) {
+        const int op = prog[2 * pc];
+        const int arg = prog[2 * pc + 1];
+        if (op == 0) {
+#pragma unroll 1
+            for (int q = 0; q < arg; q++) fp::mont_sqr<F, CANON>(acc, acc);
+        } else if (op == 1) {
+            uint32_t b[N];
+#pragma unroll
+            for (int l = 0; l < N; l++) b[l] = tbl[(arg * N + l) * stride];
+            fp::mont_mul<F, CANON>(acc, acc, b);
+        } else if (op == 2) {
+#pragma unroll
+            for (int l = 0; l < N; l++) acc[l] = tbl[(arg * N + l) * stride];
+        } else {
+#pragma unroll
+            for (int l = 0; l < N; l++) tbl[(arg * N + l) * stride] = acc[l];
+        }
+    }
+}
+
+template <class F>
+FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
+    constexpr int N = F::N;
+    uint32_t acc[N];
+    if constexpr (F::USE_PROGRAM) pow_program<F>(acc, x, tbl, stride);
+    else pow_window<F>(acc, x, tbl, stride);
+    if (F::LAZY) {  // lazy fields stay in [0, 2p + small) between multiplies (generated/fields.cuh)
         fp::cond_sub_p<F>(acc);
         if (F::FINAL_SUBS == 2) fp::cond_sub_p<F>(acc);
     }

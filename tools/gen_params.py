@@ -33,6 +33,11 @@ SPECIAL_LIMBS = {
 }
 
 
+# which exponentiation program each field runs: "window" = sliding window of WINDOW[field] bits; "reference" =
+# the reference crate's own addition chain (src/<field>/sbox.rs), used where its live set fits in shared memory
+CHAIN_SOURCE = {"pallas": "reference", "vesta": "reference"}
+
+
 def limbs(v, n, bits):
     return [(v >> (bits * i)) & ((1 << bits) - 1) for i in range(n)]
 
@@ -71,6 +76,89 @@ def sliding_window(e, w):
             nsq -= 255
         out.append((nsq, idx))
     return first, out
+
+
+# ---- exponentiation programs for the GPU ladder interpreter (anemoi_kernels.cuh: pow_inv_alpha) -------------
+# ISA: (OP_SQR, n) acc = acc^(2^n); (OP_MUL, k) acc *= T[k]; (OP_LD, k) acc = T[k]; (OP_ST, k) T[k] = acc.
+# T[] are shared-memory slots; T[0] = x on entry; the result is left in acc.
+OP_SQR, OP_MUL, OP_LD, OP_ST = 0, 1, 2, 3
+
+
+def program_from_window(first, ops, table):
+    """Sliding-window ladder: odd powers x^(2k+1) in slots 0..table-1, x^2 in slot `table` while they are built."""
+    prog = [(OP_LD, 0), (OP_SQR, 1), (OP_ST, table), (OP_LD, 0)]
+    for k in range(1, table):
+        prog += [(OP_MUL, table), (OP_ST, k)]
+    if first != table - 1:
+        prog.append((OP_LD, first))
+    for nsq, idx in ops:
+        prog.append((OP_SQR, nsq))
+        if idx >= 0:
+            prog.append((OP_MUL, idx))
+    return prog, table + 1
+
+
+def program_from_chain(chain):
+    """The reference's own addition chain (SSA pairs, value 0 = x) compiled onto an accumulator + slots by a
+    linear scan: a value is stored only if it is needed later than the very next step, slots are recycled at
+    the last use."""
+    uses = {}
+    for i, (a, b) in enumerate(chain):
+        uses.setdefault(a, []).append(i)
+        uses.setdefault(b, []).append(i)
+    slot_of, free, nslots, acc, prog = {0: 0}, [], 1, None, []
+    for i, (a, b) in enumerate(chain):
+        res = i + 1
+        if acc == a and acc == b:
+            prog.append((OP_SQR, 1))
+        elif acc == a:
+            prog.append((OP_MUL, slot_of[b]))
+        elif acc == b:
+            prog.append((OP_MUL, slot_of[a]))
+        elif a == b:
+            prog += [(OP_LD, slot_of[a]), (OP_SQR, 1)]
+        else:
+            prog += [(OP_LD, slot_of[a]), (OP_MUL, slot_of[b])]
+        acc = res
+        for v in {a, b}:
+            if max(uses[v]) == i and v in slot_of:
+                free.append(slot_of.pop(v))
+        if any(j > i + 1 for j in uses.get(res, [])):
+            if free:
+                sl = free.pop()
+            else:
+                sl = nslots
+                nslots += 1
+            slot_of[res] = sl
+            prog.append((OP_ST, sl))
+    out = []
+    for op, arg in prog:
+        if op == OP_SQR and out and out[-1][0] == OP_SQR and out[-1][1] + arg <= 255:
+            out[-1] = (OP_SQR, out[-1][1] + arg)
+        else:
+            out.append((op, arg))
+    return out, nslots
+
+
+def check_program(prog, slots, e):
+    """Run the program on exponents (T[0] = 1 = exponent of x); returns (#squarings, #multiplies)."""
+    T = [None] * slots
+    T[0] = 1
+    acc, nsq, nmul = None, 0, 0
+    for op, arg in prog:
+        if op == OP_SQR:
+            acc <<= arg
+            nsq += arg
+        elif op == OP_MUL:
+            acc += T[arg]
+            nmul += 1
+        elif op == OP_LD:
+            acc = T[arg]
+        else:
+            assert arg < slots
+            T[arg] = acc
+    assert acc == e, "program does not compute x^e"
+    return nsq, nmul
 
 
 def check_schedule(e, w, first, ops):
@@ -123,8 +211,18 @@ def main():
         first, ops = sliding_window(inv_alpha, w)
         nsq, nmul = check_schedule(inv_alpha, w, first, ops)
         table = 1 << (w - 1)
-        # table build: 1 squaring + (table-1) multiplies
-        summary[field] = {"window": w, "pow_sqr": nsq + 1, "pow_mul": nmul + table - 1,
+        use_program = CHAIN_SOURCE.get(field, "window") == "reference"
+        if use_program:
+            prog, slots = program_from_chain(fp["chain"])
+            source = "reference chain (src/%s/sbox.rs)" % field
+        else:
+            # the window ladder has its own specialised code path in the kernel (x^2 and the running odd power stay
+            # in registers while the table is built); the equivalent program is only used to count operations
+            prog, _ = program_from_window(first, ops, table)
+            slots = table
+            source = "sliding window w = %d" % w
+        psq, pmul = check_program(prog, max(slots, table + 1), inv_alpha)
+        summary[field] = {"program": source, "slots": slots, "pow_sqr": psq, "pow_mul": pmul, "prog_len": len(prog),
                           "ref_chain": len(fp["chain"])}
 
         # -p^-1 mod 2^32 is read from constant memory on the device, NOT folded as an immediate: when ptxas sees
@@ -150,15 +248,19 @@ def main():
         cu.append("    static constexpr int BYTE_CHUNK = %d;\n" % fp["byte_chunk"])
         cu.append("    static constexpr int ROUNDS_2_1 = %d;\n" % fp["inst"]["anemoi_2_1"]["rounds"])
         cu.append("    static constexpr int ROUNDS_4_3 = %d;\n" % fp["inst"]["anemoi_4_3"]["rounds"])
-        # launch geometry: (threads per block, resident blocks per SM the kernel is compiled for). The table in
-        # shared memory (TABLE*N*4 B per thread, +1 KB per block) and the register file bound residency:
-        # N = 12: 128 x 4 = 16 warps/SM (<= 128 registers; 64 x 9 = 18 warps was measured: no gain); N = 8: 128 x 6 = 24
-        # warps/SM with the 8-entry table, 128 x 3 with the 16-entry table (w = 5).
-        blk, minb = ((128, 3) if w == 5 else (128, 6)) if n32 == 8 else (128, 4)
+        # launch geometry: (threads per block, resident blocks per SM the kernel is compiled for). The ladder's
+        # slots in shared memory (SLOTS*N*4 B per thread, +1 KB per block) and the register file bound residency:
+        # N = 12: 128 x 4 = 16 warps/SM (<= 128 registers; 64 x 9 = 18 warps was measured: no gain); N = 8: up to
+        # 128 x 6 = 24 warps/SM (<= 80 registers).
+        blk = 128
+        by_smem = (227 * 1024) // (slots * n32 * 4 * blk + 1024)
+        minb = max(1, min(6 if n32 == 8 else 4, by_smem))
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
-        cu.append("    static constexpr int WINDOW = %d;\n" % w)
-        cu.append("    static constexpr int TABLE = %d;    // odd powers x^1, x^3, ..\n" % table)
+        cu.append("    static constexpr int SLOTS = %d;     // shared-memory slots of the ladder (slot 0 = x)\n" % slots)
+        cu.append("    // x^(1/alpha): %s, %d squarings + %d multiplies (reference chain: %d)\n" % (source, psq, pmul, len(fp["chain"])))
+        cu.append("    static constexpr bool USE_PROGRAM = %s;\n" % ("true" if use_program else "false"))
+        cu.append("    static constexpr int PROG_LEN = %d;\n" % (len(prog) if use_program else 0))
         cu.append("    static constexpr int SCHED_FIRST = %d;\n" % first)
         cu.append("    static constexpr int SCHED_LEN = %d;\n" % len(ops))
         # Montgomery quotient digit m = t0 * n0inv. When n0inv = -1 it is a negation, done on the ALU pipe as
@@ -174,9 +276,14 @@ def main():
         cu.append("};\n")
         # schedule + ARK tables as plain arrays (placed in __constant__ memory by the including TU)
         cu.append("#ifdef ANEMOI_FIELD_TABLES_%s\n" % field)
-        cu.append("// sliding-window schedule for x^INV_ALPHA: {squarings, table index or 255}\n")
-        cu.append("__constant__ uint8_t k_sched_%s[%d][2] = {%s};\n" % (
-            field, len(ops), ",".join("{%d,%d}" % (a, b if b >= 0 else 255) for a, b in ops)))
+        if use_program:
+            cu.append("// ladder program for x^INV_ALPHA: {op, arg}; 0 = SQR n, 1 = MUL slot, 2 = LD slot, 3 = ST slot\n")
+            cu.append("__constant__ uint8_t k_prog_%s[%d][2] = {%s};\n" % (
+                field, len(prog), ",".join("{%d,%d}" % (a, b) for a, b in prog)))
+        else:
+            cu.append("// sliding-window schedule for x^INV_ALPHA: {squarings, table index or 255}\n")
+            cu.append("__constant__ uint8_t k_prog_%s[%d][2] = {%s};\n" % (
+                field, len(ops), ",".join("{%d,%d}" % (a, b if b >= 0 else 255) for a, b in ops)))
         for inst in INSTS:
             ip = fp["inst"][inst]
             cols, rounds = ip["cols"], ip["rounds"]
@@ -193,7 +300,7 @@ def main():
                 cu.append("    " + ",".join("0x%08xu" % x for x in words[i:i + 8]) + ",\n")
             cu.append("};\n")
         cu.append("template <> struct Tables<F_%s> {\n" % field)
-        cu.append("    static __device__ __forceinline__ const uint8_t* sched() { return &k_sched_%s[0][0]; }\n" % field)
+        cu.append("    static __device__ __forceinline__ const uint8_t* prog() { return &k_prog_%s[0][0]; }\n" % field)
         cu.append("    static __device__ __forceinline__ const uint32_t* ark(int cols) { return cols == 1 ? k_ark_%s_2_1 : k_ark_%s_4_3; }\n" % (field, field))
         cu.append("};\n")
         cu.append("#endif\n\n")
