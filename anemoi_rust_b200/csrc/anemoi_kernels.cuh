@@ -61,6 +61,44 @@ FPQ void store_felt(uint32_t* p, const uint32_t (&r)[N], int vec16) {
 // (1) Sliding-window ladder (w = 4): slots hold the odd powers x, x^3, .., x^15; the schedule {squarings, slot}
 //     comes from constant memory (warp-uniform, no divergence).
 template <class F>
+FPQ void pow_window_local(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
+    constexpr int N = F::N;
+    constexpr bool CANON = !F::LAZY;
+    uint32_t T[F::SLOTS][N];  // dynamically indexed -> per-thread local memory (L1/L2), no shared memory needed
+    {
+        uint32_t x2[N], t[N];
+        fp::mont_sqr<F, CANON>(x2, x);
+#pragma unroll
+        for (int l = 0; l < N; l++) {
+            t[l] = x[l];
+            T[0][l] = x[l];
+        }
+#pragma unroll 1
+        for (int k = 1; k < F::SLOTS; k++) {
+            fp::mont_mul<F, CANON>(t, t, x2);
+#pragma unroll
+            for (int l = 0; l < N; l++) T[k][l] = t[l];
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < N; l++) acc[l] = T[F::SCHED_FIRST][l];
+    const uint8_t* sched = Tables<F>::prog();
+#pragma unroll 1
+    for (int s = 0; s < F::SCHED_LEN; s++) {
+        const int nsq = sched[2 * s];
+        const int idx = sched[2 * s + 1];
+#pragma unroll 1
+        for (int q = 0; q < nsq; q++) fp::mont_sqr<F, CANON>(acc, acc);
+        if (idx != 255) {
+            uint32_t b[N];
+#pragma unroll
+            for (int l = 0; l < N; l++) b[l] = T[idx][l];
+            fp::mont_mul<F, CANON>(acc, acc, b);
+        }
+    }
+}
+
+template <class F>
 FPQ void pow_window(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
     constexpr int N = F::N;
     constexpr bool CANON = !F::LAZY;
@@ -133,10 +171,45 @@ FPQ void pow_program(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N], uint32_t*
 }
 
 template <class F>
+FPQ void pow_program_local(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
+    constexpr int N = F::N;
+    constexpr bool CANON = !F::LAZY;
+    uint32_t T[F::SLOTS][N];  // per-thread local memory
+#pragma unroll
+    for (int l = 0; l < N; l++) {
+        acc[l] = x[l];
+        T[0][l] = x[l];
+    }
+    const uint8_t* prog = Tables<F>::prog();
+#pragma unroll 1
+    for (int pc = 0; pc < F::PROG_LEN; pc++) {
+        const int op = prog[2 * pc];
+        const int arg = prog[2 * pc + 1];
+        if (op == 0) {
+#pragma unroll 1
+            for (int q = 0; q < arg; q++) fp::mont_sqr<F, CANON>(acc, acc);
+        } else if (op == 1) {
+            uint32_t b[N];
+#pragma unroll
+            for (int l = 0; l < N; l++) b[l] = T[arg][l];
+            fp::mont_mul<F, CANON>(acc, acc, b);
+        } else if (op == 2) {
+#pragma unroll
+            for (int l = 0; l < N; l++) acc[l] = T[arg][l];
+        } else {
+#pragma unroll
+            for (int l = 0; l < N; l++) T[arg][l] = acc[l];
+        }
+    }
+}
+
+template <class F>
 FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
     constexpr int N = F::N;
     uint32_t acc[N];
-    if constexpr (F::USE_PROGRAM) pow_program<F>(acc, x, tbl, stride);
+    if constexpr (F::USE_PROGRAM && F::LOCAL_TABLE) pow_program_local<F>(acc, x);
+    else if constexpr (F::USE_PROGRAM) pow_program<F>(acc, x, tbl, stride);
+    else if constexpr (F::LOCAL_TABLE) pow_window_local<F>(acc, x);
     else pow_window<F>(acc, x, tbl, stride);
     if (F::LAZY) {  // lazy fields stay in [0, 2p + small) between multiplies (generated/fields.cuh)
         fp::cond_sub_p<F>(acc);

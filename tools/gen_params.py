@@ -21,7 +21,7 @@ INSTS = ["anemoi_2_1", "anemoi_4_3"]
 # sliding-window width per field for the GPU exponentiation (odd-power table of 2^(w-1) entries kept
 # in shared memory: entries * N * 4 bytes per thread). Measured on B200: w = 5 (16 entries, half the resident
 # warps) wins by 1-2 % on Pallas/Vesta, is neutral on ed_on_bls12_377/jubjub and loses on bls12_381 2-1.
-WINDOW = {"bls12_377": 4, "bls12_381": 4, "bn_254": 4, "ed_on_bls12_377": 4, "jubjub": 4, "pallas": 5, "vesta": 5}
+WINDOW = {"bls12_377": 5, "bls12_381": 5, "bn_254": 4, "ed_on_bls12_377": 5, "jubjub": 5, "pallas": 5, "vesta": 5}
 
 
 # limbs of p (value 0, 1 or 2^k) diverted from IMAD.WIDE to ALU adds/shifts in the reduction rows. Measured on
@@ -253,8 +253,10 @@ def main():
         # N = 12: 128 x 4 = 16 warps/SM (<= 128 registers; 64 x 9 = 18 warps was measured: no gain); N = 8: up to
         # 128 x 6 = 24 warps/SM (<= 80 registers).
         blk = 128
-        by_smem = (227 * 1024) // (slots * n32 * 4 * blk + 1024)
+        local_table = True
+        by_smem = 99 if local_table else (227 * 1024) // (slots * n32 * 4 * blk + 1024)
         minb = max(1, min(6 if n32 == 8 else 4, by_smem))
+        cu.append("    static constexpr bool LOCAL_TABLE = %s;\n" % ("true" if local_table else "false"))
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
         cu.append("    static constexpr int SLOTS = %d;     // shared-memory slots of the ladder (slot 0 = x)\n" % slots)
