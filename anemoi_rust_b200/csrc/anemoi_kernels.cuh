@@ -8,9 +8,9 @@
 //
 // Mapping: Anemoi-2-1 (1 column) -> 1 thread per state; Anemoi-4-3 (2 columns) -> 2 adjacent lanes per
 // state, which exchange their columns with warp shuffles for the linear layer (the two S-boxes of a
-// round, > 99 % of the work, are independent). x^(1/alpha) uses a sliding-window ladder over a
-// compile-time schedule (any chain gives the same canonical residue as the reference's hard-coded
-// chain); the odd-power table lives in shared memory, column-major per thread (bank-conflict-free).
+// round, > 99 % of the work, are independent). x^(1/alpha) runs a per-field ladder (sliding window or the
+// reference's own addition chain -- any chain gives the same canonical residue) whose table lives in
+// per-thread local memory.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -54,17 +54,19 @@ FPQ void store_felt(uint32_t* p, const uint32_t (&r)[N], int vec16) {
 }
 
 // x^INV_ALPHA -- replaces sbox::exp_by_inv_alpha (src/<field>/sbox.rs). Any addition chain yields the same
-// canonical residue as the reference's hard-coded one, so each field runs the cheapest ladder whose live set fits
-// in shared memory (tools/gen_params.py). tbl points at this thread's column of the shared-memory slots:
-// slot k, limb l at tbl[(k*N + l) * stride].
+// canonical residue as the reference's hard-coded one, so each field runs whichever ladder measured fastest
+// (tools/gen_params.py). The ladder's table / slots are a dynamically indexed per-thread array, i.e. LOCAL
+// memory (L1/L2-backed): one 32/48-byte entry is touched per ~5 squarings (~5 k cycles per thread), so its
+// latency is irrelevant, while shared memory would cap the resident warps (8 entries x 48 B x 512 threads =
+// 192 KB per SM) and forbid the larger tables. Measured: +2-5 % on every field against the shared-memory table.
 //
-// (1) Sliding-window ladder (w = 4): slots hold the odd powers x, x^3, .., x^15; the schedule {squarings, slot}
-//     comes from constant memory (warp-uniform, no divergence).
+// (1) Sliding-window ladder: T[k] = x^(2k+1); the schedule {squarings, entry} comes from constant memory
+//     (warp-uniform, no divergence). x^2 and the running odd power stay in registers while T is built.
 template <class F>
-FPQ void pow_window_local(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
+FPQ void pow_window(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
     constexpr int N = F::N;
     constexpr bool CANON = !F::LAZY;
-    uint32_t T[F::SLOTS][N];  // dynamically indexed -> per-thread local memory (L1/L2), no shared memory needed
+    uint32_t T[F::SLOTS][N];
     {
         uint32_t x2[N], t[N];
         fp::mont_sqr<F, CANON>(x2, x);
@@ -98,83 +100,15 @@ FPQ void pow_window_local(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
     }
 }
 
+// (2) Accumulator machine running the reference crate's own addition chain, compiled onto slots by a linear-scan
+//     allocator in tools/gen_params.py: SQR n, MUL slot, LD slot, ST slot; slot 0 = x. Used where it measured
+//     faster than the window ladder: bls12_381 (378 S + 76 M in 28 slots vs 379 S + 81 M), Pallas (252 S + 43 M in
+//     11 slots vs 250 S + 56 M), Vesta (248 S + 45 M in 12 slots).
 template <class F>
-FPQ void pow_window(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
+FPQ void pow_program(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
     constexpr int N = F::N;
     constexpr bool CANON = !F::LAZY;
-    {
-        uint32_t x2[N], t[N];
-        fp::mont_sqr<F, CANON>(x2, x);
-#pragma unroll
-        for (int l = 0; l < N; l++) {
-            t[l] = x[l];
-            tbl[l * stride] = x[l];
-        }
-#pragma unroll 1
-        for (int k = 1; k < F::SLOTS; k++) {
-            fp::mont_mul<F, CANON>(t, t, x2);
-#pragma unroll
-            for (int l = 0; l < N; l++) tbl[(k * N + l) * stride] = t[l];
-        }
-    }
-#pragma unroll
-    for (int l = 0; l < N; l++) acc[l] = tbl[(F::SCHED_FIRST * N + l) * stride];
-    const uint8_t* sched = Tables<F>::prog();
-#pragma unroll 1
-    for (int s = 0; s < F::SCHED_LEN; s++) {
-        const int nsq = sched[2 * s];
-        const int idx = sched[2 * s + 1];
-#pragma unroll 1
-        for (int q = 0; q < nsq; q++) fp::mont_sqr<F, CANON>(acc, acc);
-        if (idx != 255) {
-            uint32_t b[N];
-#pragma unroll
-            for (int l = 0; l < N; l++) b[l] = tbl[(idx * N + l) * stride];
-            fp::mont_mul<F, CANON>(acc, acc, b);
-        }
-    }
-}
-
-// (2) Accumulator machine running the reference crate's own addition chain, compiled onto slots by
-//     tools/gen_params.py (Pallas: 252 S + 43 M in 11 slots, Vesta: 248 S + 45 M in 12 slots, against 250 S + 56 M
-//     for the best window ladder): SQR n, MUL slot, LD slot, ST slot; slot 0 = x.
-template <class F>
-FPQ void pow_program(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
-    constexpr int N = F::N;
-    constexpr bool CANON = !F::LAZY;
-#pragma unroll
-    for (int l = 0; l < N; l++) {
-        acc[l] = x[l];
-        tbl[l * stride] = x[l];
-    }
-    const uint8_t* prog = Tables<F>::prog();
-#pragma unroll 1
-    for (int pc = 0; pc < F::PROG_LEN; pc++) {
-        const int op = prog[2 * pc];
-        const int arg = prog[2 * pc + 1];
-        if (op == 0) {
-#pragma unroll 1
-            for (int q = 0; q < arg; q++) fp::mont_sqr<F, CANON>(acc, acc);
-        } else if (op == 1) {
-            uint32_t b[N];
-#pragma unroll
-            for (int l = 0; l < N; l++) b[l] = tbl[(arg * N + l) * stride];
-            fp::mont_mul<F, CANON>(acc, acc, b);
-        } else if (op == 2) {
-#pragma unroll
-            for (int l = 0; l < N; l++) acc[l] = tbl[(arg * N + l) * stride];
-        } else {
-#pragma unroll
-            for (int l = 0; l < N; l++) tbl[(arg * N + l) * stride] = acc[l];
-        }
-    }
-}
-
-template <class F>
-FPQ void pow_program_local(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
-    constexpr int N = F::N;
-    constexpr bool CANON = !F::LAZY;
-    uint32_t T[F::SLOTS][N];  // per-thread local memory
+    uint32_t T[F::SLOTS][N];
 #pragma unroll
     for (int l = 0; l < N; l++) {
         acc[l] = x[l];
@@ -204,13 +138,11 @@ FPQ void pow_program_local(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
 }
 
 template <class F>
-FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t* tbl, int stride) {
+FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N]) {
     constexpr int N = F::N;
     uint32_t acc[N];
-    if constexpr (F::USE_PROGRAM && F::LOCAL_TABLE) pow_program_local<F>(acc, x);
-    else if constexpr (F::USE_PROGRAM) pow_program<F>(acc, x, tbl, stride);
-    else if constexpr (F::LOCAL_TABLE) pow_window_local<F>(acc, x);
-    else pow_window<F>(acc, x, tbl, stride);
+    if constexpr (F::USE_PROGRAM) pow_program<F>(acc, x);
+    else pow_window<F>(acc, x);
     if (F::LAZY) {  // lazy fields stay in [0, 2p + small) between multiplies (generated/fields.cuh)
         fp::cond_sub_p<F>(acc);
         if (F::FINAL_SUBS == 2) fp::cond_sub_p<F>(acc);
@@ -222,13 +154,13 @@ FPQ void pow_inv_alpha(uint32_t (&r)[F::N], const uint32_t (&x)[F::N], uint32_t*
 // Anemoi::sbox_layer for this thread's column (src/traits.rs:328-358):
 //   x -= beta*y^2;  y -= x^(1/alpha);  x += beta*y^2 + delta
 template <class F>
-FPQ void sbox_column(uint32_t (&x)[F::N], uint32_t (&y)[F::N], uint32_t* tbl, int stride) {
+FPQ void sbox_column(uint32_t (&x)[F::N], uint32_t (&y)[F::N]) {
     constexpr int N = F::N;
     uint32_t t[N], g[N];
     fp::mont_sqr<F, true>(t, y);
     fp::mul_by_beta<F>(g, t);
     fp::sub_mod<F>(x, x, g);
-    pow_inv_alpha<F>(t, x, tbl, stride);
+    pow_inv_alpha<F>(t, x);
     fp::sub_mod<F>(y, y, t);
     fp::mont_sqr<F, true>(t, y);
     fp::mul_by_beta<F>(g, t);
@@ -277,7 +209,7 @@ FPQ void linear_layer(uint32_t (&x)[F::N], uint32_t (&y)[F::N], int col, unsigne
 }
 
 template <class F, int COLS>
-FPQ void permutation(uint32_t (&x)[F::N], uint32_t (&y)[F::N], int col, unsigned pair_mask, uint32_t* tbl, int stride) {
+FPQ void permutation(uint32_t (&x)[F::N], uint32_t (&y)[F::N], int col, unsigned pair_mask) {
     constexpr int N = F::N;
     constexpr int ROUNDS = (COLS == 1) ? F::ROUNDS_2_1 : F::ROUNDS_4_3;
 #pragma unroll 1
@@ -292,7 +224,7 @@ FPQ void permutation(uint32_t (&x)[F::N], uint32_t (&y)[F::N], int col, unsigned
         for (int l = 0; l < N; l++) k[l] = c[N + l];
         fp::add_mod<F>(y, y, k);
         linear_layer<F, COLS>(x, y, col, pair_mask);
-        sbox_column<F>(x, y, tbl, stride);
+        sbox_column<F>(x, y);
     }
     linear_layer<F, COLS>(x, y, col, pair_mask);
 }
@@ -331,10 +263,6 @@ template <class F, int COLS>
 __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelArgs a) {
     constexpr int N = F::N;
     constexpr int W = 2 * COLS;
-    extern __shared__ uint32_t smem[];
-    const int stride = blockDim.x;
-    uint32_t* tbl = smem + threadIdx.x;
-
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long unit = t / COLS;
     const int col = (int)(t % COLS);
@@ -422,8 +350,8 @@ __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelA
                 }
             }
         }
-        if (mode == MODE_SBOX) sbox_column<F>(x, y, tbl, stride);
-        else permutation<F, COLS>(x, y, col, pair_mask, tbl, stride);
+        if (mode == MODE_SBOX) sbox_column<F>(x, y);
+        else permutation<F, COLS>(x, y, col, pair_mask);
     }
 
     // ---- epilogue

@@ -20,15 +20,7 @@ static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     const int block = (threads >= (unsigned long long)sms * F::BLOCK * 2) ? F::BLOCK : 32;
     const unsigned long long blocks = (threads + block - 1) / block;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
-    const size_t smem = F::LOCAL_TABLE ? 0 : (size_t)F::SLOTS * F::N * sizeof(uint32_t) * block;
-    static bool attr_set[64] = {};
-    if (device < 64 && !attr_set[device]) {
-        cudaError_t e = cudaFuncSetAttribute(anemoi_kernel<F, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)((size_t)F::SLOTS * F::N * sizeof(uint32_t) * F::BLOCK));
-        if (e != cudaSuccess) return e;
-        attr_set[device] = true;
-    }
-    anemoi_kernel<F, COLS><<<(unsigned)blocks, block, smem, stream>>>(a);
+    anemoi_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -18,9 +18,9 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 FIELDS = ["bls12_377", "bls12_381", "bn_254", "ed_on_bls12_377", "jubjub", "pallas", "vesta"]
 INSTS = ["anemoi_2_1", "anemoi_4_3"]
 
-# sliding-window width per field for the GPU exponentiation (odd-power table of 2^(w-1) entries kept
-# in shared memory: entries * N * 4 bytes per thread). Measured on B200: w = 5 (16 entries, half the resident
-# warps) wins by 1-2 % on Pallas/Vesta, is neutral on ed_on_bls12_377/jubjub and loses on bls12_381 2-1.
+# sliding-window width per field for the GPU exponentiation (odd-power table of 2^(w-1) entries, in per-thread
+# local memory: entries * N * 4 bytes per thread). w = 5 minimises squarings + multiplies for every field but
+# bn_254.
 WINDOW = {"bls12_377": 5, "bls12_381": 5, "bn_254": 4, "ed_on_bls12_377": 5, "jubjub": 5, "pallas": 5, "vesta": 5}
 
 
@@ -33,9 +33,13 @@ SPECIAL_LIMBS = {
 }
 
 
-# which exponentiation program each field runs: "window" = sliding window of WINDOW[field] bits; "reference" =
-# the reference crate's own addition chain (src/<field>/sbox.rs), used where its live set fits in shared memory
-CHAIN_SOURCE = {"pallas": "reference", "vesta": "reference"}
+# which exponentiation program each field runs: "window" = sliding window of WINDOW[field] bits (specialised code
+# path); "reference" = the reference crate's own addition chain (src/<field>/sbox.rs) on the accumulator machine.
+# Measured on B200 with the slots in local memory (ms per 2^20 states, 2-1 / 4-3):
+#   bls12_381  reference 277.2 / 373.3   window-5 281.9 / 372.8      bn_254  reference 92.1 / 123.2  window-4 89.4 / 122.2
+#   jubjub     reference  89.0 / 118.2   window-5  88.6 / 117.8      ed_on   reference 78.9 / 107.2  window-5 79.0 / 106.5
+#   pallas / vesta: reference 82.8 / 109.5, 82.4 / 109.0 (window-5 with shared-memory slots: 88.0 / 115.9)
+CHAIN_SOURCE = {"pallas": "reference", "vesta": "reference", "bls12_381": "reference"}
 
 
 def limbs(v, n, bits):
@@ -249,17 +253,13 @@ def main():
         cu.append("    static constexpr int ROUNDS_2_1 = %d;\n" % fp["inst"]["anemoi_2_1"]["rounds"])
         cu.append("    static constexpr int ROUNDS_4_3 = %d;\n" % fp["inst"]["anemoi_4_3"]["rounds"])
         # launch geometry: (threads per block, resident blocks per SM the kernel is compiled for). The ladder's
-        # slots in shared memory (SLOTS*N*4 B per thread, +1 KB per block) and the register file bound residency:
-        # N = 12: 128 x 4 = 16 warps/SM (<= 128 registers; 64 x 9 = 18 warps was measured: no gain); N = 8: up to
-        # 128 x 6 = 24 warps/SM (<= 80 registers).
+        # slots live in local memory, so only the register file bounds residency: N = 12: 128 x 4 = 16 warps/SM
+        # (<= 128 registers; 18 and 20 warps were measured: no gain); N = 8: 128 x 6 = 24 warps/SM (<= 80 registers).
         blk = 128
-        local_table = True
-        by_smem = 99 if local_table else (227 * 1024) // (slots * n32 * 4 * blk + 1024)
-        minb = max(1, min(6 if n32 == 8 else 4, by_smem))
-        cu.append("    static constexpr bool LOCAL_TABLE = %s;\n" % ("true" if local_table else "false"))
+        minb = 6 if n32 == 8 else 4
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
-        cu.append("    static constexpr int SLOTS = %d;     // shared-memory slots of the ladder (slot 0 = x)\n" % slots)
+        cu.append("    static constexpr int SLOTS = %d;     // local-memory slots of the ladder (slot 0 = x)\n" % slots)
         cu.append("    // x^(1/alpha): %s, %d squarings + %d multiplies (reference chain: %d)\n" % (source, psq, pmul, len(fp["chain"])))
         cu.append("    static constexpr bool USE_PROGRAM = %s;\n" % ("true" if use_program else "false"))
         cu.append("    static constexpr int PROG_LEN = %d;\n" % (len(prog) if use_program else 0))
