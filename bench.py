@@ -263,7 +263,11 @@ def main():
     roofline = {
         "bound": "imad", "achieved": achieved * 1e-12, "peak": peak_ops * 1e-12, "unit": "TMAC32/s",
         "frac": achieved / peak_ops,
-        "traffic": 130668544,   # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/)
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r1_ncu_full_bls12_381_*):
+        # 3.66 GB read + 15.62 GB written. Far above the 0.15 GB of algorithmic bytes ON PURPOSE: the ladder's slot
+        # table lives in per-thread local memory whose write-back reaches HBM (~70 GB/s, 1 % of the HBM peak, no
+        # time cost); the zero-traffic alternative (table in shared memory) measured 4 % slower.
+        "traffic": 19283889000,
         "kernel": "anemoi_kernel<F_bls12_381,1>", "kernel_ms": kernel_s * 1e3,
         "algorithmic_mac32_per_compress": MAC32_PER_COMPRESS,
         "algorithmic_bytes_per_launch": n * HBM_BYTES_PER_COMPRESS,
