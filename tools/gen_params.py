@@ -253,10 +253,11 @@ def main():
         cu.append("    static constexpr int ROUNDS_2_1 = %d;\n" % fp["inst"]["anemoi_2_1"]["rounds"])
         cu.append("    static constexpr int ROUNDS_4_3 = %d;\n" % fp["inst"]["anemoi_4_3"]["rounds"])
         # launch geometry: (threads per block, resident blocks per SM the kernel is compiled for). The ladder's
-        # slots live in local memory, so only the register file bounds residency: N = 12: 128 x 4 = 16 warps/SM
-        # (<= 128 registers; 18 and 20 warps were measured: no gain); N = 8: 128 x 6 = 24 warps/SM (<= 80 registers).
+        # slots live in local memory, so only the register file bounds residency: N = 12: 128 x 5 = 20 warps/SM
+        # (<= 96 registers, no spills); N = 8: 128 x 7 = 28 warps/SM (<= 72 registers, no spills). One block fewer
+        # measured 0-1.5 % slower.
         blk = 128
-        minb = 6 if n32 == 8 else 4
+        minb = 7 if n32 == 8 else 5
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
         cu.append("    static constexpr int SLOTS = %d;     // local-memory slots of the ladder (slot 0 = x)\n" % slots)
