@@ -226,9 +226,9 @@ FPQ void madc_row_rshift(uint32_t* odd, const uint32_t* a, uint32_t b) {
 
 // m * p rows with the modulus limbs as compile-time constants. Limbs that are 0, 1 or a power of two
 // (p[0] = 1 for five of the seven fields; Pallas/Vesta: p = 2^254 + t with p[4..6] = 0, p[7] = 2^30) do not
-// need a multiplier: they become add-with-carry / shift instructions on the ALU pipe, which is idle while the
-// FMA-heavy pipe is saturated by IMAD.WIDE. SPECIAL_LIMBS selects how many of them are diverted (balance
-// between the two pipes; 0 = all limbs go through IMAD.WIDE).
+// need a multiplier: they can become add-with-carry / shift instructions on the ALU pipe while the FMA-heavy
+// pipe is saturated by IMAD.WIDE. F::special_limb(j) (tools/gen_params.py: SPECIAL_LIMBS) selects which of them
+// are diverted; measured on B200, diverting p[0] = 1 helps every field that has it, diverting more does not.
 HD constexpr bool fp_is_pow2(uint32_t v) { return v != 0 && (v & (v - 1)) == 0; }
 HD constexpr int fp_log2(uint32_t v) { return v <= 1 ? 0 : 1 + fp_log2(v >> 1); }
 
