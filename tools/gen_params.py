@@ -351,10 +351,12 @@ def main():
     oc.append("};\n\n#endif\n")
 
     os.makedirs(os.path.join(ROOT, "anemoi_rust_b200", "csrc", "generated"), exist_ok=True)
-    with open(os.path.join(ROOT, "anemoi_rust_b200", "csrc", "generated", "fields.cuh"), "w") as f:
-        f.write("".join(cu))
-    with open(os.path.join(ROOT, "oracle", "params_gen.h"), "w") as f:
-        f.write("".join(oc))
+    for path, text in ((os.path.join(ROOT, "anemoi_rust_b200", "csrc", "generated", "fields.cuh"), "".join(cu)),
+                       (os.path.join(ROOT, "oracle", "params_gen.h"), "".join(oc))):
+        old = open(path).read() if os.path.exists(path) else None
+        if old != text:  # leave the mtime alone when nothing changed (avoids needless rebuilds)
+            with open(path, "w") as f:
+                f.write(text)
     for k, v in summary.items():
         print(k, v)
 
