@@ -203,3 +203,35 @@ def test_adversarial_limb_patterns(field, inst):
     x = np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(f.n64)] for v in vals], dtype=np.uint64)
     assert np.array_equal(H.permutation_batch(x), C.permute(fi, ii, x))
     assert np.array_equal(H.compress_k_batch(x, W), C.compress(fi, ii, W, x))
+
+
+def test_full_size_cross_mode_properties_4_3():
+    """Size-independent identities on a 2^20-state Pallas Anemoi-4-3 batch (BASELINE config 3's node function):
+    compress_k(.,4) = compress(.)[0] + compress(.)[1]  (anemoi_4_3/hasher.rs:148-179), and
+    hash_field of a 3-element message = permutation([e0, e1, e2, 0])[0]  (hasher.rs:93-129, sigma = 1)."""
+    H = A.AnemoiPallas_4_3
+    f = H.FIELD
+    n = 1 << 20
+    x = f.random_mont(4 * n, SEED + 70)
+    k4 = H.compress_k_batch(x, 4)
+    k2 = H.compress_k_batch(x, 2)
+    rng = np.random.default_rng(11)
+    idx = np.sort(rng.choice(n, size=4096, replace=False))
+    a = f.decode(k2.reshape(n, 2, f.n64)[idx, 0])
+    b = f.decode(k2.reshape(n, 2, f.n64)[idx, 1])
+    c = f.decode(k4[idx])
+    assert all((u + v) % f.p == w for u, v, w in zip(a, b, c))
+    # sponge vs permutation on 2^16 messages of 3 elements
+    m = 1 << 16
+    msgs = x[: 3 * m].reshape(m, 3, f.n64)
+    states = np.zeros((m, 4, f.n64), dtype=np.uint64)
+    states[:, :3] = msgs
+    perm = H.permutation_batch(states.reshape(-1, f.n64)).reshape(m, 4, f.n64)
+    assert np.array_equal(H.hash_field_batch(msgs), perm[:, 0])
+    # 2-1: hash_field of a 1-element message = permutation([e, 0])[0]; of 2 elements = two chained permutations
+    H2 = A.AnemoiBls12_381_2_1
+    f2 = H2.FIELD
+    e = f2.random_mont(1 << 14, SEED + 71)
+    st = np.zeros((1 << 14, 2, f2.n64), dtype=np.uint64)
+    st[:, 0] = e
+    assert np.array_equal(H2.hash_field_batch(e.reshape(-1, 1, f2.n64)), H2.permutation_batch(st.reshape(-1, f2.n64)).reshape(-1, 2, f2.n64)[:, 0])
