@@ -385,4 +385,43 @@ __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelA
     }
 }
 
+// Diagnostic kernel: ONE layer of the round function on a batch of states, in place -- the reference exposes
+// ark_layer / mds_layer / sbox_layer / round as trait methods (src/traits.rs:113-157, 328-367); this lets each of
+// them be compared with the oracle in isolation. a.mode = MODE_LAYER_ARK / MDS / ROUND, a.len = round index.
+// (Kept apart from anemoi_kernel so that the hot kernel's code and register allocation are untouched.)
+template <class F, int COLS>
+__global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_layer_kernel(KernelArgs a) {
+    constexpr int N = F::N;
+    constexpr int W = 2 * COLS;
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long unit = t / COLS;
+    const int col = (int)(t % COLS);
+    const bool active = unit < a.n;
+    if (!active) unit = a.n - 1;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned pair_mask = (COLS == 2) ? (3u << (lane & ~1u)) : 0xffffffffu;
+    uint32_t x[N], y[N];
+    const uint32_t* s = a.in + unit * (W * N);
+    load_felt<N>(x, s + col * N, a.vec16);
+    load_felt<N>(y, s + (COLS + col) * N, a.vec16);
+    if (a.mode == MODE_LAYER_ARK || a.mode == MODE_LAYER_ROUND) {
+        // Anemoi::ark_layer (src/traits.rs:113-125)
+        const uint32_t* c = Tables<F>::ark(COLS) + (((int)a.len * COLS + col) * 2) * N;
+        uint32_t k[N];
+#pragma unroll
+        for (int l = 0; l < N; l++) k[l] = c[l];
+        fp::add_mod<F>(x, x, k);
+#pragma unroll
+        for (int l = 0; l < N; l++) k[l] = c[N + l];
+        fp::add_mod<F>(y, y, k);
+    }
+    if (a.mode == MODE_LAYER_MDS || a.mode == MODE_LAYER_ROUND) linear_layer<F, COLS>(x, y, col, pair_mask);
+    if (a.mode == MODE_LAYER_ROUND) sbox_column<F>(x, y);
+    if (active) {
+        uint32_t* d = a.out + unit * (W * N);
+        store_felt<N>(d + col * N, x, a.vec16);
+        store_felt<N>(d + (COLS + col) * N, y, a.vec16);
+    }
+}
+
 }  // namespace anemoi

@@ -268,6 +268,18 @@ int anemoi_b200_sbox_layer_dev(int field, int inst, uint64_t* d_states, size_t n
     return launch(field, inst, anemoi::MODE_SBOX, d_states, d_states, nullptr, n, 0, (cudaStream_t)stream);
 }
 
+int anemoi_b200_layer_dev(int field, int inst, int layer, int round, uint64_t* d_states, size_t n, void* stream) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (layer < 0 || layer > 3) return ANEMOI_B200_ERR_ARG;
+    // assert!(round_ctr < Self::NUM_ROUNDS)  src/traits.rs:115
+    if ((layer == 0 || layer == 3) && (round < 0 || round >= kRounds[field][inst])) return ANEMOI_B200_ERR_LENGTH;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!d_states) return ANEMOI_B200_ERR_ARG;
+    const int modes[4] = {anemoi::MODE_LAYER_ARK, anemoi::MODE_LAYER_MDS, anemoi::MODE_SBOX, anemoi::MODE_LAYER_ROUND};
+    return launch(field, inst, modes[layer], d_states, d_states, nullptr, n, (size_t)(round < 0 ? 0 : round), (cudaStream_t)stream);
+}
+
 int anemoi_b200_compress_dev(int field, int inst, int k, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream) {
     int rc = check_fi(field, inst);
     if (rc) return rc;
@@ -487,6 +499,19 @@ int anemoi_b200_sbox_layer(int field, int inst, uint64_t* states, size_t n, int 
     const size_t bytes = n * width_of(inst) * felt_bytes(field);
     return host_call(device, states, bytes, states, bytes, true, [&](void* di, void*, cudaStream_t st) {
         return anemoi_b200_sbox_layer_dev(field, inst, (uint64_t*)di, n, st);
+    });
+}
+
+int anemoi_b200_layer(int field, int inst, int layer, int round, uint64_t* states, size_t n, int device) {
+    int rc = check_fi(field, inst);
+    if (rc) return rc;
+    if (layer < 0 || layer > 3) return ANEMOI_B200_ERR_ARG;
+    if ((layer == 0 || layer == 3) && (round < 0 || round >= kRounds[field][inst])) return ANEMOI_B200_ERR_LENGTH;
+    if (n == 0) return ANEMOI_B200_OK;
+    if (!states) return ANEMOI_B200_ERR_ARG;
+    const size_t bytes = n * width_of(inst) * felt_bytes(field);
+    return host_call(device, states, bytes, states, bytes, true, [&](void* di, void*, cudaStream_t st) {
+        return anemoi_b200_layer_dev(field, inst, layer, round, (uint64_t*)di, n, st);
     });
 }
 

@@ -20,7 +20,10 @@ static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     const int block = (threads >= (unsigned long long)sms * F::BLOCK * 2) ? F::BLOCK : 32;
     const unsigned long long blocks = (threads + block - 1) / block;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
-    anemoi_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
+    if (a.mode >= MODE_LAYER_ARK)
+        anemoi_layer_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
+    else
+        anemoi_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,10 @@ enum Mode : int {
     MODE_MERGE43 = 7,      // 4-3 sponge merge: [d0, d0, 0, 0] (sic, reference ignores d1)
     MODE_TO_BYTES = 8,     // digest.to_bytes: de-Montgomery, one felt per unit (no permutation)
     MODE_HASH_BYTES_RAGGED = 9,  // sponge hash (bytes), byte offsets[]
+    // diagnostic single-layer modes (anemoi_layer_kernel)
+    MODE_LAYER_ARK = 10,    // ark_layer(state, round = len)
+    MODE_LAYER_MDS = 11,    // mds_layer(state)
+    MODE_LAYER_ROUND = 12,  // round(state, round = len) = ark -> mds -> sbox
 };
 
 struct KernelArgs {

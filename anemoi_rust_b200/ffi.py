@@ -49,6 +49,8 @@ _SIGS = {
     "anemoi_b200_field_name": ([_i], ctypes.c_char_p),
     "anemoi_b200_permute": ([_i, _i, _vp, _sz, _i], _i),
     "anemoi_b200_sbox_layer": ([_i, _i, _vp, _sz, _i], _i),
+    "anemoi_b200_layer": ([_i, _i, _i, _i, _vp, _sz, _i], _i),
+    "anemoi_b200_layer_dev": ([_i, _i, _i, _i, _vp, _sz, _vp], _i),
     "anemoi_b200_compress": ([_i, _i, _i, _vp, _vp, _sz, _i], _i),
     "anemoi_b200_compress_multi": ([_i, _i, _i, _vp, _vp, _sz, _i], _i),
     "anemoi_b200_hash_field": ([_i, _i, _vp, _sz, _sz, _vp, _i], _i),

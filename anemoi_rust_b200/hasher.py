@@ -146,6 +146,18 @@ class _AnemoiBase:
         return a
 
     @classmethod
+    def layer_batch(cls, states, layer, round_ctr=0):
+        """One layer on n states (host array in, new array out): 'ark' (needs round_ctr), 'mds', 'sbox',
+        'round' (needs round_ctr) -- Anemoi::{ark_layer, mds_layer, sbox_layer, round}, src/traits.rs:113-367."""
+        f, W = cls.FIELD, cls.STATE_WIDTH
+        code = {"ark": 0, "mds": 1, "sbox": 2, "round": 3}[layer]
+        a = _np_in(states, f.n64).copy()
+        if a.size % (W * f.n64):
+            raise ffi.LengthError(ffi.ERR_LENGTH, "not a whole number of states")
+        ffi.check(_lib.anemoi_b200_layer(f.id, cls.INST, code, round_ctr, _ptr(a), a.size // (W * f.n64), cls.device))
+        return a
+
+    @classmethod
     def compress_k_batch(cls, states, k, out=None, n_gpus=1):
         """Jive::compress_k on n states: (n*W felts) -> (n*W/k felts). n_gpus > 1 (host arrays only) splits the
         batch over that many devices of this process; independent states need no collective."""

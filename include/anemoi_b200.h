@@ -79,6 +79,12 @@ int anemoi_b200_permute(int field, int inst, uint64_t* states, size_t n, int dev
  * reference's test_sbox vectors (src/<field>/anemoi_x/mod.rs test_sbox) pin. */
 int anemoi_b200_sbox_layer(int field, int inst, uint64_t* states, size_t n, int device);
 
+/* One layer of the round function on n states, in place (diagnostic; the reference exposes these as trait
+ * methods): layer 0 = Anemoi::ark_layer(state, round) (src/traits.rs:113-125), 1 = Anemoi::mds_layer
+ * (:129-157), 2 = Anemoi::sbox_layer (:328-358), 3 = Anemoi::round(state, round) (:361-367).
+ * round >= NUM_ROUNDS -> ERR_LENGTH (the reference asserts, traits.rs:115). */
+int anemoi_b200_layer(int field, int inst, int layer, int round, uint64_t* states, size_t n, int device);
+
 /* Jive::compress / Jive::compress_k on n states.
  *   inst 2-1: k must be 2 (src/<field>/anemoi_2_1/hasher.rs:96-110); out = n elements.
  *   inst 4-3: k in {2, 4} (src/<field>/anemoi_4_3/hasher.rs:148-179); out = n * (4/k) elements.
@@ -132,6 +138,7 @@ int anemoi_b200_digest_to_bytes(int field, const uint64_t* digests, uint8_t* byt
 /* ---- device-pointer, stream-ordered entry points (current device) -------------------------- */
 int anemoi_b200_permute_dev(int field, int inst, uint64_t* d_states, size_t n, void* stream);
 int anemoi_b200_sbox_layer_dev(int field, int inst, uint64_t* d_states, size_t n, void* stream);
+int anemoi_b200_layer_dev(int field, int inst, int layer, int round, uint64_t* d_states, size_t n, void* stream);
 int anemoi_b200_compress_dev(int field, int inst, int k, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream);
 int anemoi_b200_hash_field_dev(int field, int inst, const uint64_t* d_elems, size_t n_msgs, size_t felts_per_msg,
                                uint64_t* d_digests, void* stream);

@@ -385,6 +385,22 @@ int oracle_sbox_layer(int field, int inst, uint64_t* states, size_t n_states) {
     return 0;
 }
 
+/* One layer in isolation: 0 = ark_layer(round), 1 = mds_layer, 2 = sbox_layer, 3 = round(round) (traits.rs:113-367) */
+int oracle_layer(int field, int inst, int layer, int round, uint64_t* states, size_t n_states) {
+    ctx_t c;
+    if (make_ctx(&c, field, inst)) return -1;
+    if (layer < 0 || layer > 3) return -1;
+    if ((layer == 0 || layer == 3) && (round < 0 || round >= c.rounds)) return -5;
+    const size_t stride = (size_t)c.width * c.n;
+    for (size_t i = 0; i < n_states; i++) {
+        uint64_t* s = states + i * stride;
+        if (layer == 0 || layer == 3) ark_layer(s, round, &c);
+        if (layer == 1 || layer == 3) mds_layer(s, &c);
+        if (layer == 2 || layer == 3) DISPATCH(&c, sbox4(s, &c), sbox6(s, &c));
+    }
+    return 0;
+}
+
 int oracle_compress(int field, int inst, int k, const uint64_t* in, uint64_t* out, size_t n_states) {
     ctx_t c;
     if (make_ctx(&c, field, inst)) return -1;

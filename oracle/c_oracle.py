@@ -31,6 +31,7 @@ def lib():
         _lib.oracle_permute.argtypes = [i, i, vp, sz]
         _lib.oracle_sbox_layer.argtypes = [i, i, vp, sz]
         _lib.oracle_compress.argtypes = [i, i, i, vp, vp, sz]
+        _lib.oracle_layer.argtypes = [i, i, i, i, vp, sz]
         _lib.oracle_hash_field.argtypes = [i, i, vp, sz, sz, vp]
         _lib.oracle_hash_field_ragged.argtypes = [i, i, vp, vp, sz, vp]
         _lib.oracle_hash_bytes.argtypes = [i, i, vp, sz, sz, vp]
@@ -69,6 +70,13 @@ def sbox_layer(fi, inst, states):
     a = np.ascontiguousarray(states, dtype=np.uint64).copy()
     W = 2 if inst == 0 else 4
     _chk(lib().oracle_sbox_layer(fi, inst, _p(a), a.size // (W * N64[fi])))
+    return a
+
+
+def layer(fi, inst, which, round_ctr, states):
+    a = np.ascontiguousarray(states, dtype=np.uint64).copy()
+    W = 2 if inst == 0 else 4
+    _chk(lib().oracle_layer(fi, inst, which, round_ctr, _p(a), a.size // (W * N64[fi])))
     return a
 
 

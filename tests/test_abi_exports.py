@@ -17,7 +17,7 @@ def declared_functions():
 
 def test_header_symbols_are_exported():
     names = declared_functions()
-    assert len(names) >= 38
+    assert len(names) >= 40
     lib = ctypes.CDLL(os.path.join(ROOT, "anemoi_rust_b200", "libanemoi_b200.so"))
     for n in names:
         assert hasattr(lib, n), "libanemoi_b200.so does not export " + n

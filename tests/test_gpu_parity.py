@@ -235,3 +235,30 @@ def test_full_size_cross_mode_properties_4_3():
     st = np.zeros((1 << 14, 2, f2.n64), dtype=np.uint64)
     st[:, 0] = e
     assert np.array_equal(H2.hash_field_batch(e.reshape(-1, 1, f2.n64)), H2.permutation_batch(st.reshape(-1, f2.n64)).reshape(-1, 2, f2.n64)[:, 0])
+
+
+@pytest.mark.parametrize("field,inst", CASES)
+def test_layers_in_isolation(field, inst):
+    """Anemoi::{ark_layer, mds_layer, sbox_layer, round} one at a time on random states vs the oracle, and the
+    composition ark -> mds -> sbox == round; round >= NUM_ROUNDS is rejected like the reference's assert."""
+    H = HASHERS[(field, inst)]
+    fi, ii = ids(field, inst)
+    f, W = H.FIELD, H.STATE_WIDTH
+    x = f.random_mont(W * 301, SEED + 90)
+    for r in (0, 3, H.NUM_HASH_ROUNDS - 1):
+        a = H.layer_batch(x, "ark", r)
+        assert np.array_equal(a, C.layer(fi, ii, 0, r, x))
+        m = H.layer_batch(a, "mds")
+        assert np.array_equal(m, C.layer(fi, ii, 1, 0, a))
+        s = H.layer_batch(m, "sbox")
+        assert np.array_equal(s, C.layer(fi, ii, 2, 0, m))
+        assert np.array_equal(H.layer_batch(x, "round", r), s)
+        assert np.array_equal(s, C.layer(fi, ii, 3, r, x))
+    with pytest.raises(A.LengthError):
+        H.layer_batch(x, "round", H.NUM_HASH_ROUNDS)
+    # the whole permutation = NUM_ROUNDS rounds + one more mds_layer (traits.rs:370-378)
+    y = x[: W * 5].copy()
+    for r in range(H.NUM_HASH_ROUNDS):
+        y = H.layer_batch(y, "round", r)
+    y = H.layer_batch(y, "mds")
+    assert np.array_equal(y, H.permutation_batch(x[: W * 5]))

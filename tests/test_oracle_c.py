@@ -90,3 +90,25 @@ def test_ragged_and_threads():
     got = dec("bn_254", C.hash_field_ragged(fi, ii, enc("bn_254", flat), offs))
     assert got == [R.hash_field(P, m) for m in msgs]
     assert C.max_threads() >= 1
+
+
+@pytest.mark.parametrize("field,inst", CASES)
+def test_layers_vs_bigint(field, inst):
+    """ark_layer / mds_layer / round in isolation: C oracle == big-integer oracle (they are pinned by the
+    reference's vectors only transitively, through hash/jive)."""
+    fi, ii = R.FIELDS.index(field), R.INSTS.index(inst)
+    P = R.params(field, inst)
+    rng = random.Random(7 + fi)
+    s0 = [rng.randrange(P.p) for _ in range(P.width)]
+    for r in (0, 1, P.rounds - 1):
+        s = list(s0)
+        R.ark(P, s, r)
+        assert dec(field, C.layer(fi, ii, 0, r, enc(field, s0))) == s
+        s = list(s0)
+        R.ark(P, s, r)
+        R.mds(P, s)
+        R.sbox(P, s)
+        assert dec(field, C.layer(fi, ii, 3, r, enc(field, s0))) == s
+    s = list(s0)
+    R.mds(P, s)
+    assert dec(field, C.layer(fi, ii, 1, 0, enc(field, s0))) == s
