@@ -4,8 +4,11 @@
 // CPU implementation of any hash function in this library.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -14,6 +17,7 @@
 #include "kernel_args.h"
 #include "launch.h"
 #include "merkle_aux.h"
+#include "nccl_dyn.h"
 
 namespace {
 
@@ -93,23 +97,53 @@ int jive_mode(int inst, int k, int* out_per_state) {
     return ANEMOI_B200_ERR_ARITY;
 }
 
-// Device buffers of the host-pointer entry points come from the device's stream-ordered memory pool with
-// an unlimited release threshold, so repeated calls reuse the same HBM without cudaMalloc/cudaFree round
-// trips (those cost ~10 ms each at 100 MiB and would dominate the copy time).
+// Device buffers of the host-pointer entry points come from a stream-ordered memory pool OWNED BY THIS LIBRARY
+// (one per device, created on first use under std::call_once, release threshold = keep everything), so repeated
+// calls reuse the same HBM without cudaMalloc/cudaFree round trips (~10 ms each at 100 MiB) and without touching
+// the device's default pool, which other allocators of the process (e.g. PyTorch's) may be using.
+// anemoi_b200_pool_trim() hands the cached memory back.
+constexpr int kMaxDevices = 64;
+std::once_flag g_pool_once[kMaxDevices];
+cudaMemPool_t g_pool[kMaxDevices] = {};
+
+cudaMemPool_t library_pool(int device) {
+    if (device < 0 || device >= kMaxDevices) return nullptr;
+    std::call_once(g_pool_once[device], [device]() {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+            unsigned long long threshold = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+            g_pool[device] = pool;
+        } else {
+            cudaGetLastError();  // no pool support: DevBuf falls back to cudaMalloc
+        }
+    });
+    return g_pool[device];
+}
+
 struct DevBuf {
     void* p = nullptr;
     cudaStream_t st = nullptr;
     bool async = false;
-    ~DevBuf() {
+    ~DevBuf() { release(); }
+    void release() {
         if (!p) return;
         if (async) cudaFreeAsync(p, st);
         else cudaFree(p);
+        p = nullptr;
     }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
     cudaError_t alloc_async(size_t bytes, cudaStream_t stream) {
+        int device = 0;
+        cudaGetDevice(&device);
+        cudaMemPool_t pool = library_pool(device);
         st = stream;
         async = true;
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, stream);
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, pool, stream) : cudaErrorNotSupported;
         if (e != cudaSuccess) {  // pool unsupported / exhausted: plain allocation
             cudaGetLastError();
             async = false;
@@ -119,19 +153,6 @@ struct DevBuf {
         return e;
     }
 };
-
-void keep_pool_memory(int device) {
-    static bool done[64] = {};
-    if (device < 0 || device >= 64 || done[device]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long threshold = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    } else {
-        cudaGetLastError();
-    }
-    done[device] = true;
-}
 
 struct DeviceScope {
     int prev = -1;
@@ -162,7 +183,6 @@ template <class Body>
 int host_call(int device, const void* in, size_t in_bytes, void* out, size_t out_bytes, bool in_place, Body body) {
     DeviceScope scope(device);
     if (scope.rc != ANEMOI_B200_OK) return scope.rc;
-    keep_pool_memory(device);
     cudaStream_t stream;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = ANEMOI_B200_OK;
@@ -213,11 +233,22 @@ const char* anemoi_b200_strerror(int code) {
         case ANEMOI_B200_ERR_CUDA: return "CUDA runtime error (see anemoi_b200_last_cuda_error)";
         case ANEMOI_B200_ERR_NO_DEVICE: return "no CUDA device available (this library has no CPU fallback)";
         case ANEMOI_B200_ERR_NOMEM: return "device memory allocation failed";
+        case ANEMOI_B200_ERR_NCCL: return "NCCL error or libnccl.so.2 not loadable (see anemoi_b200_last_cuda_error)";
     }
     return "unknown error code";
 }
 
 const char* anemoi_b200_last_cuda_error(void) { return g_cuda_err; }
+
+int anemoi_b200_pool_trim(int device, size_t keep_bytes) {
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    cudaMemPool_t pool = library_pool(device);
+    if (!pool) return ANEMOI_B200_OK;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemPoolTrimTo(pool, keep_bytes));
+    return ANEMOI_B200_OK;
+}
 
 int anemoi_b200_device_count(void) {
     int count = 0;
@@ -590,17 +621,16 @@ int anemoi_b200_hash_field_ragged(int field, int inst, const uint64_t* elems, co
     const uint64_t base = offsets[0], total = offsets[n_msgs] - base;
     if (total && !elems) return ANEMOI_B200_ERR_ARG;
     const size_t fb = felt_bytes(field);
-    DeviceScope scope(device);
-    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
     // rebase the offsets so only the referenced element range is copied
     std::vector<uint64_t> rel(n_msgs + 1);
     for (size_t i = 0; i <= n_msgs; i++) rel[i] = offsets[i] - base;
-    DevBuf d_off;
-    CK(d_off.alloc((n_msgs + 1) * sizeof(uint64_t)));
-    CK(cudaMemcpy(d_off.p, rel.data(), (n_msgs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     const uint8_t* src = reinterpret_cast<const uint8_t*>(elems) + base * fb;
     return host_call(device, total ? src : reinterpret_cast<const uint8_t*>(rel.data()), total * fb, digests, n_msgs * fb,
                      false, [&](void* di, void* dout, cudaStream_t st) {
+                         // the offsets go up on the SAME stream as the kernel that reads them (stream-ordered)
+                         DevBuf d_off;
+                         CK(d_off.alloc_async((n_msgs + 1) * sizeof(uint64_t), st));
+                         CK(cudaMemcpyAsync(d_off.p, rel.data(), (n_msgs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
                          return anemoi_b200_hash_field_ragged_dev(field, inst, (const uint64_t*)di,
                                                                   (const uint64_t*)d_off.p, n_msgs, (uint64_t*)dout, st);
                      });
@@ -630,15 +660,13 @@ int anemoi_b200_hash_bytes_ragged(int field, int inst, const uint8_t* bytes, con
         if (offsets[i + 1] < offsets[i]) return ANEMOI_B200_ERR_LENGTH;
     const uint64_t base = offsets[0], total = offsets[n_msgs] - base;
     if (total && !bytes) return ANEMOI_B200_ERR_ARG;
-    DeviceScope scope(device);
-    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
     std::vector<uint64_t> rel(n_msgs + 1);
     for (size_t i = 0; i <= n_msgs; i++) rel[i] = offsets[i] - base;
-    DevBuf d_off;
-    CK(d_off.alloc((n_msgs + 1) * sizeof(uint64_t)));
-    CK(cudaMemcpy(d_off.p, rel.data(), (n_msgs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     const void* src = total ? (const void*)(bytes + base) : (const void*)rel.data();
     return host_call(device, src, total, digests, n_msgs * felt_bytes(field), false, [&](void* di, void* dout, cudaStream_t st) {
+        DevBuf d_off;  // same stream as the kernel that reads it
+        CK(d_off.alloc_async((n_msgs + 1) * sizeof(uint64_t), st));
+        CK(cudaMemcpyAsync(d_off.p, rel.data(), (n_msgs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         return anemoi_b200_hash_bytes_ragged_dev(field, inst, (const uint8_t*)di, (const uint64_t*)d_off.p, n_msgs,
                                                  (uint64_t*)dout, st);
     });
@@ -666,22 +694,181 @@ int anemoi_b200_digest_to_bytes(int field, const uint64_t* digests, uint8_t* byt
     });
 }
 
+// ---- sharded Merkle root: per-rank sub-tree, ONE NCCL all-gather of the partial roots, top levels on every rank ----
+
+}  // extern "C"
+
+namespace {
+
+// How a tree of world * n_local leaves splits over `world` contiguous slices: each rank reduces
+// `local_levels` levels (while its slice is whole sub-trees), leaving `roots_per_rank` partial roots; the gathered
+// world * roots_per_rank partial roots must form a complete tree of `top_levels` levels.
+struct ShardPlan {
+    int local_levels = 0;
+    size_t roots_per_rank = 0;
+    int top_levels = 0;
+};
+
+int shard_plan(int arity, size_t n_local, int world, ShardPlan* plan) {
+    if (n_local == 0 || world < 1) return ANEMOI_B200_ERR_LENGTH;
+    size_t m = n_local;
+    int local_levels = 0;
+    while (m > 1 && m % (size_t)arity == 0) {
+        m /= (size_t)arity;
+        local_levels++;
+    }
+    size_t t = m * (size_t)world;
+    int top_levels = 0;
+    while (t > 1) {
+        if (t % (size_t)arity) return ANEMOI_B200_ERR_LENGTH;  // the ranks do not split this tree into whole sub-trees
+        t /= (size_t)arity;
+        top_levels++;
+    }
+    plan->local_levels = local_levels;
+    plan->roots_per_rank = m;
+    plan->top_levels = top_levels;
+    return ANEMOI_B200_OK;
+}
+
+thread_local char g_nccl_err[160] = "";
+int nccl_fail(int code, const char* what) {
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, nc.ok ? nc.GetErrorString(code) : "libnccl.so.2 could not be loaded");
+    return ANEMOI_B200_ERR_NCCL;
+}
+#define NK(call)                                        \
+    do {                                                \
+        int r__ = (call);                               \
+        if (r__ != anemoi::nccl::kSuccess) return nccl_fail(r__, #call); \
+    } while (0)
+
+// Single-process communicators over devices 0..n-1 (ncclCommInitAll), created once per n and kept for the life of
+// the process (communicator setup costs ~100 ms; the all-gather itself is microseconds).
+std::mutex g_comm_mu;
+std::vector<anemoi::nccl::comm_t> g_all_comms[kMaxDevices + 1];
+
+int single_process_comms(int n_gpus, std::vector<anemoi::nccl::comm_t>* out) {
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    if (!nc.ok) return nccl_fail(-1, "NCCL");
+    std::lock_guard<std::mutex> lock(g_comm_mu);
+    std::vector<anemoi::nccl::comm_t>& c = g_all_comms[n_gpus];
+    if (c.empty()) {
+        std::vector<int> devs(n_gpus);
+        for (int g = 0; g < n_gpus; g++) devs[g] = g;
+        std::vector<anemoi::nccl::comm_t> fresh(n_gpus, nullptr);
+        NK(nc.CommInitAll(fresh.data(), n_gpus, devs.data()));
+        c = fresh;
+    }
+    *out = c;
+    return ANEMOI_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int anemoi_b200_nccl_version(void) {
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    int v = 0;
+    if (!nc.ok || !nc.GetVersion || nc.GetVersion(&v) != anemoi::nccl::kSuccess) return 0;
+    return v;
+}
+
+int anemoi_b200_comm_unique_id(uint8_t* id128) {
+    if (!id128) return ANEMOI_B200_ERR_ARG;
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    if (!nc.ok) return nccl_fail(-1, "NCCL");
+    anemoi::nccl::unique_id id;
+    NK(nc.GetUniqueId(&id));
+    memcpy(id128, id.internal, sizeof(id.internal));
+    return ANEMOI_B200_OK;
+}
+
+int anemoi_b200_comm_init_rank(const uint8_t* id128, int nranks, int rank, void** comm) {
+    if (!id128 || !comm || nranks < 1 || rank < 0 || rank >= nranks) return ANEMOI_B200_ERR_ARG;
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    if (!nc.ok) return nccl_fail(-1, "NCCL");
+    anemoi::nccl::unique_id id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    anemoi::nccl::comm_t c = nullptr;
+    NK(nc.CommInitRank(&c, nranks, id, rank));  // collective over the nranks callers; binds the CURRENT device
+    *comm = c;
+    return ANEMOI_B200_OK;
+}
+
+int anemoi_b200_comm_destroy(void* comm) {
+    if (!comm) return ANEMOI_B200_OK;
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    if (!nc.ok) return nccl_fail(-1, "NCCL");
+    NK(nc.CommDestroy((anemoi::nccl::comm_t)comm));
+    return ANEMOI_B200_OK;
+}
+
+int anemoi_b200_comm_info(void* comm, int* nranks, int* rank) {
+    if (!comm) return ANEMOI_B200_ERR_ARG;
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    if (!nc.ok) return nccl_fail(-1, "NCCL");
+    if (nranks) NK(nc.CommCount((anemoi::nccl::comm_t)comm, nranks));
+    if (rank) NK(nc.CommUserRank((anemoi::nccl::comm_t)comm, rank));
+    return ANEMOI_B200_OK;
+}
+
+size_t anemoi_b200_merkle_sharded_scratch_felts(int arity, size_t n_local, int nranks) {
+    ShardPlan plan;
+    if (arity < 2 || nranks < 1 || shard_plan(arity, n_local, nranks, &plan) != ANEMOI_B200_OK) return 0;
+    const size_t gathered = plan.roots_per_rank * (size_t)nranks;
+    return anemoi_b200_merkle_scratch_felts(arity, n_local) + plan.roots_per_rank + gathered +
+           anemoi_b200_merkle_scratch_felts(arity, gathered);
+}
+
+int anemoi_b200_merkle_root_sharded_dev(int field, int inst, int arity, const uint64_t* d_local_leaves, size_t n_local,
+                                        void* nccl_comm, uint64_t* d_scratch, uint64_t* d_root, void* stream) {
+    int rc = merkle_check(field, inst, arity);
+    if (rc) return rc;
+    if (n_local == 0) return ANEMOI_B200_ERR_LENGTH;
+    if (!d_local_leaves || !d_root) return ANEMOI_B200_ERR_ARG;
+    int world = 1;
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
+    if (nccl_comm) {
+        if (!nc.ok) return nccl_fail(-1, "NCCL");
+        NK(nc.CommCount((anemoi::nccl::comm_t)nccl_comm, &world));
+    }
+    ShardPlan plan;
+    rc = shard_plan(arity, n_local, world, &plan);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t words = (size_t)kFieldLimbs[field];
+    const size_t fb = felt_bytes(field);
+    DevBuf own;  // stream-ordered scratch from the library pool when the caller passes none
+    if (!d_scratch) {
+        cudaError_t e = own.alloc_async(anemoi_b200_merkle_sharded_scratch_felts(arity, n_local, world) * fb, st);
+        if (e != cudaSuccess) return cuda_fail(e, "scratch allocation");
+        d_scratch = (uint64_t*)own.p;
+    }
+    uint64_t* local_scratch = d_scratch;
+    uint64_t* partial = local_scratch + anemoi_b200_merkle_scratch_felts(arity, n_local) * words;
+    uint64_t* gathered = partial + plan.roots_per_rank * words;
+    uint64_t* top_scratch = gathered + plan.roots_per_rank * (size_t)world * words;
+    if (world == 1)  // whole tree on this device: roots_per_rank == 1 by construction of the plan
+        return anemoi_b200_merkle_reduce_dev(field, inst, arity, d_local_leaves, n_local, plan.local_levels + plan.top_levels,
+                                             local_scratch, d_root, st);
+    rc = anemoi_b200_merkle_reduce_dev(field, inst, arity, d_local_leaves, n_local, plan.local_levels, local_scratch, partial, st);
+    if (rc) return rc;
+    // the one exchange step of the path: <= 2 field elements (<= 96 bytes) per rank over NVLink
+    NK(nc.AllGather(partial, gathered, plan.roots_per_rank * fb, anemoi::nccl::kUint8, (anemoi::nccl::comm_t)nccl_comm, st));
+    return anemoi_b200_merkle_reduce_dev(field, inst, arity, gathered, plan.roots_per_rank * (size_t)world, plan.top_levels,
+                                         top_scratch, d_root, st);
+}
+
 int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves, uint64_t* root,
                             int n_gpus) {
     int rc = merkle_check(field, inst, arity);
     if (rc) return rc;
-    if (n_leaves == 0) return ANEMOI_B200_ERR_LENGTH;
     int height = 0;
-    {
-        size_t m = n_leaves;
-        while (m > 1) {
-            if (m % (size_t)arity) return ANEMOI_B200_ERR_LENGTH;  // must be arity^h
-            m /= (size_t)arity;
-            height++;
-        }
-    }
+    rc = tree_height(arity, n_leaves, &height);  // n_leaves must be arity^h
+    if (rc) return rc;
     if (!leaves || !root) return ANEMOI_B200_ERR_ARG;
-    if (n_gpus < 1 || (n_gpus & (n_gpus - 1))) return ANEMOI_B200_ERR_ARG;
+    if (n_gpus < 1 || (n_gpus & (n_gpus - 1)) || n_gpus > kMaxDevices) return ANEMOI_B200_ERR_ARG;
     const int count = anemoi_b200_device_count();
     if (count == 0) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "no CUDA device");
@@ -691,77 +878,76 @@ int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leav
     if ((size_t)n_gpus > n_leaves) n_gpus = 1;
     const size_t fb = felt_bytes(field);
     const size_t words = (size_t)kFieldLimbs[field];
-    // each GPU reduces its contiguous slice as far as whole sub-trees allow
     const size_t slice = n_leaves / (size_t)n_gpus;
-    int local_levels = 0;
-    {
-        size_t m = slice;
-        while (m > 1 && m % (size_t)arity == 0) {
-            m /= (size_t)arity;
-            local_levels++;
-        }
+    ShardPlan plan;
+    rc = shard_plan(arity, slice, n_gpus, &plan);
+    if (rc) return rc;
+    std::vector<anemoi::nccl::comm_t> comms(n_gpus, nullptr);
+    if (n_gpus > 1) {
+        rc = single_process_comms(n_gpus, &comms);
+        if (rc) return rc;
     }
-    size_t roots_per_gpu = slice;
-    for (int l = 0; l < local_levels; l++) roots_per_gpu /= (size_t)arity;
-    const size_t n_partial = roots_per_gpu * (size_t)n_gpus;
-    std::vector<uint64_t> partial(n_partial * words);
-    std::vector<int> rcs(n_gpus, ANEMOI_B200_OK);
-    std::vector<std::string> errs(n_gpus);
-
-    auto worker = [&](int g) {
-        rcs[g] = [&]() -> int {
-            DeviceScope scope(g);
-            if (scope.rc != ANEMOI_B200_OK) return scope.rc;
-            DevBuf d_leaves, d_scratch, d_out;
-            CK(d_leaves.alloc(slice * fb));
-            CK(d_scratch.alloc(anemoi_b200_merkle_scratch_felts(arity, slice) * fb));
-            CK(d_out.alloc(roots_per_gpu * fb));
-            cudaStream_t st;
-            CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            int r = ANEMOI_B200_OK;
-            cudaError_t e = cudaMemcpyAsync(d_leaves.p, leaves + (size_t)g * slice * words, slice * fb, cudaMemcpyHostToDevice, st);
-            if (e != cudaSuccess) r = cuda_fail(e, "H2D leaves");
-            if (!r)
-                r = anemoi_b200_merkle_reduce_dev(field, inst, arity, (const uint64_t*)d_leaves.p, slice, local_levels,
-                                                  (uint64_t*)d_scratch.p, (uint64_t*)d_out.p, st);
-            if (!r) {
-                e = cudaMemcpyAsync(partial.data() + (size_t)g * roots_per_gpu * words, d_out.p, roots_per_gpu * fb,
-                                    cudaMemcpyDeviceToHost, st);
-                if (e != cudaSuccess) r = cuda_fail(e, "D2H partial roots");
-            }
-            e = cudaStreamSynchronize(st);
-            if (!r && e != cudaSuccess) r = cuda_fail(e, "cudaStreamSynchronize");
-            cudaStreamDestroy(st);
-            return r;
-        }();
-        errs[g] = g_cuda_err;
+    // one host thread + stream per device. Phase 1: device buffers (library pool) + H2D of the slice. Phase 2 (only when
+    // every device got through phase 1, so that no rank is missing from the collective): sub-tree, all-gather, top levels
+    // -- redundantly on every device, as in the multi-process form; device 0 returns the root.
+    struct PerDevice {
+        cudaStream_t st = nullptr;
+        DevBuf leaves, root;
+        int rc = ANEMOI_B200_OK;
+        std::string err;
     };
-    if (n_gpus == 1) {
-        worker(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int g = 0; g < n_gpus; g++) th.emplace_back(worker, g);
-        for (auto& t : th) t.join();
-    }
-    for (int g = 0; g < n_gpus; g++)
-        if (rcs[g]) {
-            snprintf(g_cuda_err, sizeof(g_cuda_err), "gpu %d: %s", g, errs[g].c_str());
-            return rcs[g];
+    std::vector<PerDevice> dev(n_gpus);
+    auto run_phase = [&](int phase) {
+        auto body = [&](int g) {
+            PerDevice& d = dev[g];
+            d.rc = [&]() -> int {
+                DeviceScope scope(g);
+                if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+                if (phase == 1) {
+                    CK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
+                    cudaError_t e = d.leaves.alloc_async(slice * fb, d.st);
+                    if (e == cudaSuccess) e = d.root.alloc_async(fb, d.st);
+                    if (e != cudaSuccess) return cuda_fail(e, "device allocation");
+                    CK(cudaMemcpyAsync(d.leaves.p, leaves + (size_t)g * slice * words, slice * fb, cudaMemcpyHostToDevice, d.st));
+                    return ANEMOI_B200_OK;
+                }
+                int r = anemoi_b200_merkle_root_sharded_dev(field, inst, arity, (const uint64_t*)d.leaves.p, slice, comms[g], nullptr,
+                                                            (uint64_t*)d.root.p, d.st);
+                cudaError_t e = cudaSuccess;
+                if (!r && g == 0 && (e = cudaMemcpyAsync(root, d.root.p, fb, cudaMemcpyDeviceToHost, d.st)) != cudaSuccess)
+                    r = cuda_fail(e, "D2H root");
+                e = cudaStreamSynchronize(d.st);
+                if (!r && e != cudaSuccess) r = cuda_fail(e, "cudaStreamSynchronize");
+                return r;
+            }();
+            d.err = g_cuda_err;
+        };
+        if (n_gpus == 1) {
+            body(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < n_gpus; g++) th.emplace_back(body, g);
+            for (auto& t : th) t.join();
         }
-    if (n_partial == 1) {
-        memcpy(root, partial.data(), fb);
-        return ANEMOI_B200_OK;
+        for (int g = 0; g < n_gpus; g++)
+            if (dev[g].rc) {
+                snprintf(g_cuda_err, sizeof(g_cuda_err), "gpu %d: %s", g, dev[g].err.c_str());
+                return dev[g].rc;
+            }
+        return (int)ANEMOI_B200_OK;
+    };
+    rc = run_phase(1);
+    if (!rc) rc = run_phase(2);
+    for (int g = 0; g < n_gpus; g++) {  // stream-ordered frees, then the streams
+        PerDevice& d = dev[g];
+        if (!d.st) continue;
+        DeviceScope scope(g);
+        d.leaves.release();
+        d.root.release();
+        cudaStreamSynchronize(d.st);
+        cudaStreamDestroy(d.st);
     }
-    // top of the tree on device 0
-    const int top_levels = height - local_levels;
-    DeviceScope scope(0);
-    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
-    DevBuf d_scratch;
-    CK(d_scratch.alloc(anemoi_b200_merkle_scratch_felts(arity, n_partial) * fb));
-    return host_call(0, partial.data(), n_partial * fb, root, fb, false, [&](void* di, void* dout, cudaStream_t st) {
-        return anemoi_b200_merkle_reduce_dev(field, inst, arity, (const uint64_t*)di, n_partial, top_levels,
-                                             (uint64_t*)d_scratch.p, (uint64_t*)dout, st);
-    });
+    return rc;
 }
 
 int anemoi_b200_merkle_open(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves,
@@ -781,7 +967,6 @@ int anemoi_b200_merkle_open(int field, int inst, int arity, const uint64_t* leav
     }
     DeviceScope scope(device);
     if (scope.rc != ANEMOI_B200_OK) return scope.rc;
-    keep_pool_memory(device);
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     {
@@ -827,7 +1012,6 @@ int anemoi_b200_merkle_verify(int field, int inst, int arity, const uint64_t* le
     }
     DeviceScope scope(device);
     if (scope.rc != ANEMOI_B200_OK) return scope.rc;
-    keep_pool_memory(device);
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     {

@@ -3,10 +3,28 @@
 // Each field is its own TU so that nvcc compiles the seven of them in parallel and each gets its own
 // constant bank for the ARK tables.
 #pragma once
+#include <atomic>
+
 #include "anemoi_kernels.cuh"
 #include "launch.h"
 
 namespace anemoi {
+
+// SM count of the current device, looked up once per device (the attribute query costs microseconds, which is what
+// the tiny upper Merkle levels consist of).
+static inline int cached_sm_count() {
+    static std::atomic<int> cache[64];
+    int device = 0;
+    cudaGetDevice(&device);
+    if (device < 0 || device >= 64) return 148;
+    int sms = cache[device].load(std::memory_order_relaxed);
+    if (sms == 0) {
+        sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cache[device].store(sms, std::memory_order_relaxed);
+    }
+    return sms;
+}
 
 template <class F, int COLS>
 static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
@@ -14,9 +32,7 @@ static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     const unsigned long long threads = a.n * COLS;
     // Big batches: F::BLOCK-thread blocks, F::MIN_BLOCKS resident per SM. Small batches (upper Merkle levels,
     // KATs): one warp per block so the few warps spread over all SMs.
-    int device = 0, sms = 148;
-    cudaGetDevice(&device);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int sms = cached_sm_count();
     const int block = (threads >= (unsigned long long)sms * F::BLOCK * 2) ? F::BLOCK : 32;
     const unsigned long long blocks = (threads + block - 1) / block;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libanemoi_b200.so")
 
 OK = 0
-ERR_ARG, ERR_FIELD, ERR_INST, ERR_ARITY, ERR_LENGTH, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7, -8
+ERR_ARG, ERR_FIELD, ERR_INST, ERR_ARITY, ERR_LENGTH, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7, -8, -9
 
 
 class AnemoiError(RuntimeError):
@@ -71,6 +71,14 @@ _SIGS = {
     "anemoi_b200_digest_to_bytes_dev": ([_i, _vp, _vp, _sz, _vp], _i),
     "anemoi_b200_merkle_reduce_dev": ([_i, _i, _i, _vp, _sz, _i, _vp, _vp, _vp], _i),
     "anemoi_b200_merkle_scratch_felts": ([_i, _sz], _sz),
+    "anemoi_b200_merkle_root_sharded_dev": ([_i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp], _i),
+    "anemoi_b200_merkle_sharded_scratch_felts": ([_i, _sz, _i], _sz),
+    "anemoi_b200_nccl_version": ([], _i),
+    "anemoi_b200_comm_unique_id": ([_vp], _i),
+    "anemoi_b200_comm_init_rank": ([_vp, _i, _i, ctypes.POINTER(ctypes.c_void_p)], _i),
+    "anemoi_b200_comm_info": ([_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)], _i),
+    "anemoi_b200_comm_destroy": ([_vp], _i),
+    "anemoi_b200_pool_trim": ([_i, _sz], _i),
     "anemoi_b200_merkle_tree_felts": ([_i, _sz], _sz),
     "anemoi_b200_merkle_tree_dev": ([_i, _i, _i, _vp, _sz, _vp, _vp], _i),
     "anemoi_b200_merkle_open_dev": ([_i, _i, _i, _vp, _vp, _sz, _vp, _sz, _vp, _vp], _i),
@@ -91,7 +99,7 @@ def check(rc):
     if rc == OK:
         return
     text = lib.anemoi_b200_strerror(rc).decode()
-    if rc in (ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM):
+    if rc in (ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL):
         detail = lib.anemoi_b200_last_cuda_error().decode()
         if detail:
             text += " [" + detail + "]"

@@ -57,6 +57,24 @@ def _stream_of(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+def _on_device_of(t):
+    """The `_dev` entry points launch on the CURRENT device: make the tensor's device current around the call."""
+    import torch
+
+    return torch.cuda.device(t.device)
+
+
+def _check_torch_out(out, like, numel):
+    if out.device != like.device or out.dtype != like.dtype or not out.is_contiguous() or out.numel() != numel:
+        raise ValueError("`out` must be a contiguous %s tensor of %d limbs on %s" % (like.dtype, numel, like.device))
+
+
+def _check_np_out(out, numel):
+    if not (isinstance(out, np.ndarray) and out.dtype == np.uint64 and out.flags.c_contiguous and out.flags.writeable
+            and out.size == numel):
+        raise ValueError("`out` must be a writable C-contiguous uint64 array of %d limbs" % numel)
+
+
 class AnemoiDigest:
     """`AnemoiDigest([Felt; 1])` -- src/<field>/anemoi_*/digest.rs:13-53."""
 
@@ -127,8 +145,10 @@ class _AnemoiBase:
         if _is_torch(states):
             t = _torch_args(states)
             n = t.numel() // (W * f.n64)
-            assert t.numel() == n * W * f.n64
-            ffi.check(_lib.anemoi_b200_permute_dev(f.id, cls.INST, ctypes.c_void_p(t.data_ptr()), n, _stream_of(t)))
+            if t.numel() != n * W * f.n64:
+                raise ffi.LengthError(ffi.ERR_LENGTH, "not a whole number of states")
+            with _on_device_of(t):
+                ffi.check(_lib.anemoi_b200_permute_dev(f.id, cls.INST, ctypes.c_void_p(t.data_ptr()), n, _stream_of(t)))
             return t
         a = _np_in(states, f.n64).copy()
         if a.size % (W * f.n64):
@@ -174,8 +194,11 @@ class _AnemoiBase:
                 raise ffi.LengthError(ffi.ERR_LENGTH, "not a whole number of states")
             if out is None:
                 out = torch.empty((n * per, f.n64), dtype=t.dtype, device=t.device)
-            ffi.check(_lib.anemoi_b200_compress_dev(f.id, cls.INST, k, ctypes.c_void_p(t.data_ptr()),
-                                                    ctypes.c_void_p(out.data_ptr()), n, _stream_of(t)))
+            else:
+                _check_torch_out(out, t, n * per * f.n64)
+            with _on_device_of(t):
+                ffi.check(_lib.anemoi_b200_compress_dev(f.id, cls.INST, k, ctypes.c_void_p(t.data_ptr()),
+                                                        ctypes.c_void_p(out.data_ptr()), n, _stream_of(t)))
             return out
         a = _np_in(states, f.n64)
         if a.size % (W * f.n64):
@@ -183,6 +206,8 @@ class _AnemoiBase:
         n = a.size // (W * f.n64)
         if out is None:
             out = np.empty((n * per, f.n64), dtype=np.uint64)
+        else:
+            _check_np_out(out, n * per * f.n64)
         if n_gpus > 1:
             ffi.check(_lib.anemoi_b200_compress_multi(f.id, cls.INST, k, _ptr(a), _ptr(out), n, n_gpus))
         else:
@@ -203,21 +228,29 @@ class _AnemoiBase:
             import torch
 
             t = _torch_args(elems)
+            if t.numel() % f.n64:
+                raise ffi.LengthError(ffi.ERR_LENGTH, "tensor is not a whole number of field elements")
             if offsets is not None:
                 o = _torch_args(offsets)
+                if o.device != t.device:
+                    raise ValueError("offsets and elems must live on the same device")
                 n = o.numel() - 1
                 out = torch.empty((n, f.n64), dtype=t.dtype, device=t.device)
-                ffi.check(_lib.anemoi_b200_hash_field_ragged_dev(
-                    f.id, cls.INST, ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(o.data_ptr()), n,
-                    ctypes.c_void_p(out.data_ptr()), _stream_of(t)))
+                with _on_device_of(t):
+                    ffi.check(_lib.anemoi_b200_hash_field_ragged_dev(
+                        f.id, cls.INST, ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(o.data_ptr()), n,
+                        ctypes.c_void_p(out.data_ptr()), _stream_of(t)))
                 return out
             if felts_per_msg is None:
                 assert t.dim() == 3
                 felts_per_msg = t.shape[1]
+            if felts_per_msg and t.numel() % (felts_per_msg * f.n64):
+                raise ffi.LengthError(ffi.ERR_LENGTH, "not a whole number of messages of felts_per_msg elements")
             n = t.numel() // (felts_per_msg * f.n64) if felts_per_msg else (n_msgs or 0)
             out = torch.empty((n, f.n64), dtype=t.dtype, device=t.device)
-            ffi.check(_lib.anemoi_b200_hash_field_dev(f.id, cls.INST, ctypes.c_void_p(t.data_ptr()), n, felts_per_msg,
-                                                      ctypes.c_void_p(out.data_ptr()), _stream_of(t)))
+            with _on_device_of(t):
+                ffi.check(_lib.anemoi_b200_hash_field_dev(f.id, cls.INST, ctypes.c_void_p(t.data_ptr()), n, felts_per_msg,
+                                                          ctypes.c_void_p(out.data_ptr()), _stream_of(t)))
             return out
         a = _np_in(elems, f.n64)
         if offsets is not None:
@@ -231,6 +264,8 @@ class _AnemoiBase:
             felts_per_msg = a.shape[1]
             n = a.shape[0]
         else:
+            if felts_per_msg and a.size % (felts_per_msg * f.n64):
+                raise ffi.LengthError(ffi.ERR_LENGTH, "not a whole number of messages of felts_per_msg elements")
             n = a.size // (felts_per_msg * f.n64) if felts_per_msg else (n_msgs or 0)
         out = np.empty((n, f.n64), dtype=np.uint64)
         if a.size == 0:
@@ -248,6 +283,8 @@ class _AnemoiBase:
             assert a.ndim == 2
             n, bytes_per_msg = a.shape
         else:
+            if bytes_per_msg and a.size % bytes_per_msg:
+                raise ffi.LengthError(ffi.ERR_LENGTH, "not a whole number of messages of bytes_per_msg bytes")
             n = a.size // bytes_per_msg if bytes_per_msg else 1
         out = np.empty((n, f.n64), dtype=np.uint64)
         ffi.check(_lib.anemoi_b200_hash_bytes(f.id, cls.INST, _ptr(a), n, bytes_per_msg, _ptr(out), cls.device))

@@ -6,8 +6,9 @@ anemoi_4_3/hasher.rs:162-179), iterated level by level, left to right.
 
 Sharding: rank g holds leaves [g*n/G, (g+1)*n/G), reduces its slice while it still
 consists of whole sub-trees (no communication), then ONE all-gather of the partial roots (<= a few
-hundred bytes) and every rank finishes the top levels redundantly. PyTorch is only plumbing here
-(device buffers, streams, the process group); all hashing is the CUDA kernels behind the C ABI."""
+hundred bytes) and every rank finishes the top levels redundantly. The whole sharded build, NCCL
+all-gather included, is one C-ABI call (anemoi_b200_merkle_root_sharded_dev) that a Rust host reaches the
+same way; PyTorch is only plumbing here (device buffers, streams, the bootstrap of the communicator)."""
 import ctypes
 
 from . import ffi
@@ -59,10 +60,11 @@ def merkle_reduce(H, leaves, levels, scratch=None, out=None):
     if scratch is None:
         scratch = torch.empty((_lib.anemoi_b200_merkle_scratch_felts(arity, n), f.n64), dtype=leaves.dtype,
                               device=leaves.device)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(leaves.device).cuda_stream)
-    ffi.check(_lib.anemoi_b200_merkle_reduce_dev(f.id, H.INST, arity, ctypes.c_void_p(leaves.data_ptr()), n, levels,
-                                                 ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(out.data_ptr()),
-                                                 stream))
+    with torch.cuda.device(leaves.device):  # the _dev entry points launch on the CURRENT device
+        stream = ctypes.c_void_p(torch.cuda.current_stream(leaves.device).cuda_stream)
+        ffi.check(_lib.anemoi_b200_merkle_reduce_dev(f.id, H.INST, arity, ctypes.c_void_p(leaves.data_ptr()), n, levels,
+                                                     ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                     stream))
     return out
 
 
@@ -75,20 +77,72 @@ def merkle_root_device(H, leaves, scratch=None):
     return merkle_reduce(H, leaves, levels, scratch=scratch)
 
 
-def merkle_root_distributed(H, local_leaves, group=None, reduce_fn=None, scratch=None):
-    """Sharded root: every rank passes its contiguous slice; returns the (identical) root on every rank.
-    `reduce_fn(H, tensor, levels)` is injectable so the host logic (plan + all-gather + top levels) can be
-    exercised on CPU/gloo in tests; the product path always uses the CUDA `merkle_reduce`."""
+_COMMS = {}   # id(process group) -> ncclComm_t created through the C ABI (kept for the life of the process)
+
+
+def nccl_comm(group=None):
+    """The library-side NCCL communicator of a torch.distributed process group (one rank per GPU). torch is only
+    the bootstrap here: rank 0 draws an NCCL unique id through the C ABI, the 128 bytes are broadcast over the
+    process group, and every rank joins with anemoi_b200_comm_init_rank -- exactly what a Rust host would do with
+    its own transport. The communicator then belongs to libanemoi_b200.so; the all-gather of the sharded Merkle
+    build is issued by the library on the caller's stream."""
     import torch
     import torch.distributed as dist
 
-    reduce_fn = reduce_fn or merkle_reduce
+    key = id(group) if group is not None else 0
+    if key in _COMMS:
+        return _COMMS[key]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ident = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (ctypes.c_uint8 * 128)()
+        ffi.check(_lib.anemoi_b200_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+        ident = torch.tensor(list(buf), dtype=torch.uint8)
+    ident = ident.to(dev)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(ident, src=src, group=group)
+    raw = bytes(ident.cpu().tolist())
+    comm = ctypes.c_void_p()
+    ffi.check(_lib.anemoi_b200_comm_init_rank(ctypes.c_char_p(raw), world, rank, ctypes.byref(comm)))
+    n, r = ctypes.c_int(), ctypes.c_int()
+    ffi.check(_lib.anemoi_b200_comm_info(comm, ctypes.byref(n), ctypes.byref(r)))
+    assert (n.value, r.value) == (world, rank)
+    _COMMS[key] = comm
+    return comm
+
+
+def merkle_root_distributed(H, local_leaves, group=None, reduce_fn=None, scratch=None):
+    """Sharded root: every rank passes its contiguous slice (a CUDA tensor); returns the (identical) root on every
+    rank. Product path: ONE C-ABI call, anemoi_b200_merkle_root_sharded_dev (per-rank sub-tree, one ncclAllGather
+    of the <= 2 partial roots per rank issued by the library, top levels on every rank), on torch's current stream.
+    `reduce_fn(H, tensor, levels)` exists only so that the host logic (plan -> reduce -> all-gather -> top levels)
+    can be exercised on CPU/gloo in tests with the node function injected from the oracle; then the gather goes
+    through torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
     f, arity = H.FIELD, H.STATE_WIDTH
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n_local = local_leaves.numel() // f.n64
     _, local_levels, roots_per_rank, top_levels = plan(n_local * world, arity, world)
-    kw = {"scratch": scratch} if (scratch is not None and reduce_fn is merkle_reduce) else {}
-    part = reduce_fn(H, local_leaves, local_levels, **kw)
+    if reduce_fn is None:
+        if not local_leaves.is_cuda or not local_leaves.is_contiguous():
+            raise ValueError("local_leaves must be a contiguous CUDA tensor")
+        with torch.cuda.device(local_leaves.device):
+            comm = nccl_comm(group) if world > 1 else None
+            root = torch.empty((1, f.n64), dtype=local_leaves.dtype, device=local_leaves.device)
+            if scratch is not None:
+                need = _lib.anemoi_b200_merkle_sharded_scratch_felts(arity, n_local, world)
+                if scratch.numel() < need * f.n64 or scratch.device != local_leaves.device:
+                    raise ValueError("scratch must hold anemoi_b200_merkle_sharded_scratch_felts() elements on the same device")
+            stream = ctypes.c_void_p(torch.cuda.current_stream(local_leaves.device).cuda_stream)
+            ffi.check(_lib.anemoi_b200_merkle_root_sharded_dev(
+                f.id, H.INST, arity, ctypes.c_void_p(local_leaves.data_ptr()), n_local, comm,
+                ctypes.c_void_p(scratch.data_ptr()) if scratch is not None else None,
+                ctypes.c_void_p(root.data_ptr()), stream))
+        return root
+    part = reduce_fn(H, local_leaves, local_levels)
     if world == 1:
         return part if top_levels == 0 else reduce_fn(H, part, top_levels)
     gathered = torch.empty((world * roots_per_rank, f.n64), dtype=part.dtype, device=part.device)

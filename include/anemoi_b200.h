@@ -58,6 +58,7 @@ extern "C" {
 #define ANEMOI_B200_ERR_CUDA (-6)      /* a CUDA runtime call failed; see anemoi_b200_last_cuda_error() */
 #define ANEMOI_B200_ERR_NO_DEVICE (-7) /* no CUDA device: there is no CPU fallback */
 #define ANEMOI_B200_ERR_NOMEM (-8)     /* device or pinned-host allocation failed */
+#define ANEMOI_B200_ERR_NCCL (-9)      /* an NCCL call failed, or libnccl.so.2 could not be loaded at run time */
 
 /* ---- introspection ------------------------------------------------------------------------- */
 int anemoi_b200_version(void);
@@ -69,6 +70,9 @@ int anemoi_b200_state_width(int inst);         /* STATE_WIDTH: 2 or 4 (src/<fiel
 int anemoi_b200_rate_width(int inst);          /* RATE_WIDTH: 1 or 3 (mod.rs:22) */
 int anemoi_b200_num_rounds(int field, int inst); /* NUM_HASH_ROUNDS (mod.rs:31-32) */
 const char* anemoi_b200_field_name(int field); /* "bls12_377", ... (src/lib.rs module names) */
+/* Device buffers of the host-pointer calls come from a memory pool owned by this library (one per device, kept
+ * between calls). This returns all but keep_bytes of the cached memory of `device` to the driver. */
+int anemoi_b200_pool_trim(int device, size_t keep_bytes);
 
 /* ---- host-pointer entry points (synchronous) ----------------------------------------------- */
 
@@ -127,7 +131,8 @@ int anemoi_b200_merge(int field, int inst, const uint64_t* digest_pairs, uint64_
  * n_leaves must be arity^h, h >= 0 (h = 0: root = the leaf). Built level by level on the device;
  * n_gpus > 1 splits the leaves into n_gpus contiguous slices (n_gpus must be a power of two <=
  * device_count and divide n_leaves into whole sub-trees or whole groups of sub-trees), reduces each
- * slice on its own GPU concurrently, gathers the partial roots and finishes on device 0. */
+ * slice on its own GPU concurrently (one host thread + stream per device), all-gathers the partial roots with
+ * NCCL (single-process communicator, ncclCommInitAll, created once) and finishes the top levels on every device. */
 int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves, uint64_t* root,
                             int n_gpus);
 
@@ -160,6 +165,30 @@ int anemoi_b200_digest_to_bytes_dev(int field, const uint64_t* d_digests, uint8_
 int anemoi_b200_merkle_reduce_dev(int field, int inst, int arity, const uint64_t* d_leaves, size_t n_leaves, int levels,
                                   uint64_t* d_scratch, uint64_t* d_out, void* stream);
 size_t anemoi_b200_merkle_scratch_felts(int arity, size_t n_leaves);
+
+/* ---- sharded Merkle root over NCCL (north_star: "only the subtree roots are gathered over NVLink,
+ * a single tiny NCCL allgather") ---------------------------------------------------------------------------------
+ * One rank per GPU (one process or one host thread each). Rank g holds the contiguous slice
+ * [g * n_local, (g + 1) * n_local) of the leaves on its device, reduces it while it consists of whole sub-trees,
+ * all-gathers the <= 2 partial roots per rank (<= 96 bytes) with ONE ncclAllGather on `stream`, and finishes the
+ * <= 2 top levels redundantly, so every rank ends with the same root in d_root (1 element). Collective: every rank
+ * of the communicator must call it with the same field/inst/arity/n_local. nccl_comm is an ncclComm_t (from the
+ * caller's own NCCL, or from anemoi_b200_comm_init_rank); NULL = single rank (whole tree on this device).
+ * d_scratch: anemoi_b200_merkle_sharded_scratch_felts(arity, n_local, nranks) elements, or NULL to let the library
+ * take it from its stream-ordered pool. ERR_LENGTH when nranks * n_local is not a power of the arity or the ranks do
+ * not split the tree into whole sub-trees. NCCL is bound at run time (libnccl.so.2; a copy already loaded by the
+ * process, e.g. PyTorch's, is reused): ERR_NCCL if it cannot be loaded. */
+int anemoi_b200_merkle_root_sharded_dev(int field, int inst, int arity, const uint64_t* d_local_leaves, size_t n_local,
+                                        void* nccl_comm, uint64_t* d_scratch, uint64_t* d_root, void* stream);
+size_t anemoi_b200_merkle_sharded_scratch_felts(int arity, size_t n_local, int nranks);
+/* Communicator helpers so that a host without its own NCCL binding (the Rust shim) can drive the sharded build:
+ * rank 0 calls _unique_id and ships the 128 bytes to the other ranks by any means; every rank then calls
+ * _init_rank with its CUDA device current (collective). _comm_info reports (nranks, rank). */
+int anemoi_b200_nccl_version(void); /* e.g. 22809; 0 when libnccl.so.2 is not loadable */
+int anemoi_b200_comm_unique_id(uint8_t* id128);
+int anemoi_b200_comm_init_rank(const uint8_t* id128, int nranks, int rank, void** comm);
+int anemoi_b200_comm_info(void* comm, int* nranks, int* rank);
+int anemoi_b200_comm_destroy(void* comm);
 
 /* ---- Merkle trees with retained levels, authentication paths, batches of trees -------
  * Not in the reference (no tree code); node function as in anemoi_b200_merkle_root. Layouts:
