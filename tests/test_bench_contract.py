@@ -31,3 +31,31 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_other_ranks_are_silent():
     assert run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""
+
+
+def test_reference_arm_does_not_map_the_product_library(tmp_path):
+    """The reference arm must not load libanemoi_b200.so (nor import the package that dlopens it): only the oracle."""
+    script = tmp_path / "probe.py"
+    script.write_text(
+        "import sys, types\n"
+        "sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "args = types.SimpleNamespace(cpu_sample_log2=5, warmup=0, steps=1, gpus=1)\n"
+        "bench.run_reference(args, 0)\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libanemoi_oracle' in maps\n"
+        "assert 'libanemoi_b200' not in maps, 'reference arm mapped the product library'\n"
+        "assert 'anemoi_rust_b200' not in sys.modules\n"
+        "print('clean')\n" % ROOT)
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "clean" in out.stdout
+
+
+def test_traffic_hash_agrees_with_the_profiling_tool():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, ROOT)
+    import bench
+    import ncu_summary
+
+    assert bench.kernel_source_hash() == ncu_summary.kernel_source_hash()

@@ -84,3 +84,52 @@ def test_nccl_sharded_root(tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "nccl-merkle-ok" in out.stdout
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
+def test_sharded_dev_entry_with_library_communicators():
+    """anemoi_b200_merkle_root_sharded_dev driven the way a Rust host would: unique id from rank 0, every rank (here: one
+    host thread per GPU) joins with anemoi_b200_comm_init_rank and makes ONE call; all ranks end with the 1-GPU root."""
+    import ctypes
+    import threading
+
+    import torch
+
+    from anemoi_rust_b200 import ffi, merkle
+    from oracle import c_oracle as C
+
+    lib = ffi.lib
+    assert lib.anemoi_b200_nccl_version() > 0
+    for H, fi, ii, h in ((A.AnemoiPallas_4_3, 5, 1, 6), (A.AnemoiBls12_381_2_1, 1, 0, 9)):
+        f, ar = H.FIELD, H.STATE_WIDTH
+        total = ar ** h
+        leaves = f.random_mont(total, 31)
+        exp = C.merkle_root(fi, ii, ar, leaves)
+        world = 2
+        ident = (ctypes.c_uint8 * 128)()
+        ffi.check(lib.anemoi_b200_comm_unique_id(ctypes.cast(ident, ctypes.c_void_p)))
+        roots, errs = [None] * world, [None] * world
+
+        def rank_main(g):
+            try:
+                torch.cuda.set_device(g)
+                comm = ctypes.c_void_p()
+                ffi.check(lib.anemoi_b200_comm_init_rank(ctypes.cast(ident, ctypes.c_void_p), world, g, ctypes.byref(comm)))
+                sl = total // world
+                local = torch.from_numpy(leaves[g * sl:(g + 1) * sl].view(np.int64).copy()).to("cuda:%d" % g)
+                root = torch.empty((1, f.n64), dtype=torch.int64, device="cuda:%d" % g)
+                st = torch.cuda.current_stream(torch.device("cuda", g)).cuda_stream
+                ffi.check(lib.anemoi_b200_merkle_root_sharded_dev(f.id, H.INST, ar, ctypes.c_void_p(local.data_ptr()), sl, comm,
+                                                                  None, ctypes.c_void_p(root.data_ptr()), ctypes.c_void_p(st)))
+                torch.cuda.synchronize(g)
+                roots[g] = root.cpu().numpy().view(np.uint64)
+                ffi.check(lib.anemoi_b200_comm_destroy(comm))
+            except Exception as exc:  # surfaced below
+                errs[g] = exc
+
+        th = [threading.Thread(target=rank_main, args=(g,)) for g in range(world)]
+        [t.start() for t in th]
+        [t.join(timeout=300) for t in th]
+        assert errs == [None] * world, errs
+        for g in range(world):
+            assert np.array_equal(roots[g], exp), "rank %d" % g
