@@ -3,7 +3,7 @@ NVCC      ?= nvcc
 CXX       := g++
 CC        := gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -Iinclude -Xcompiler -fPIC -Xptxas -v
+NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -Iinclude -Xcompiler -fPIC -Xptxas -v $(EXTRA_NVFLAGS)
 CSRC      := anemoi_rust_b200/csrc
 FIELDS    := bls12_377 bls12_381 bn_254 ed_on_bls12_377 jubjub pallas vesta
 OBJS      := $(patsubst %,build/field_%.o,$(FIELDS)) build/api.o build/imad_peak.o build/merkle_aux.o

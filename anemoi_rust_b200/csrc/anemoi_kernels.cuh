@@ -260,7 +260,7 @@ FPQ void chunk_to_felt(uint32_t (&r)[F::N], const uint8_t* msg, unsigned long lo
 }
 
 template <class F, int COLS>
-__global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelArgs a) {
+FPQ void anemoi_body(const KernelArgs& a) {
     constexpr int N = F::N;
     constexpr int W = 2 * COLS;
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,6 +384,23 @@ __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelA
         if (active && col == 0) store_felt<N>(a.out + unit * N, x, a.vec16);
     }
 }
+
+// Throughput form: F::BLOCK-thread blocks, F::MIN_BLOCKS resident per SM (register-capped so that the FMA-heavy pipe
+// always has 16+ warps to draw from).
+template <class F, int COLS>
+__global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelArgs a) {
+    anemoi_body<F, COLS>(a);
+}
+
+#ifdef ANEMOI_LATENCY_KERNEL
+// Latency form for batches below one wave (upper Merkle levels, small API calls): one warp per block, no register cap,
+// so ptxas can schedule the multiply's independent carry chains further apart -- with a single warp per SM
+// sub-partition nothing else hides the dependent-issue latency.
+template <class F, int COLS>
+__global__ void __launch_bounds__(32, 1) anemoi_kernel_lat(KernelArgs a) {
+    anemoi_body<F, COLS>(a);
+}
+#endif
 
 // Diagnostic kernel: ONE layer of the round function on a batch of states, in place -- the reference exposes
 // ark_layer / mds_layer / sbox_layer / round as trait methods (src/traits.rs:113-157, 328-367); this lets each of

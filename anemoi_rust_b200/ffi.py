@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libanemoi_b200.so")
+# ANEMOI_B200_LIB: developer override used to A/B-test alternative BUILDS of the same library (tools/ab_variants.sh)
+LIB_PATH = os.environ.get("ANEMOI_B200_LIB") or os.path.join(_HERE, "libanemoi_b200.so")
 
 OK = 0
 ERR_ARG, ERR_FIELD, ERR_INST, ERR_ARITY, ERR_LENGTH, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7, -8, -9

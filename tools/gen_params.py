@@ -39,7 +39,13 @@ SPECIAL_LIMBS = {
 #   bls12_381  reference 277.2 / 373.3   window-5 281.9 / 372.8      bn_254  reference 92.1 / 123.2  window-4 89.4 / 122.2
 #   jubjub     reference  89.0 / 118.2   window-5  88.6 / 117.8      ed_on   reference 78.9 / 107.2  window-5 79.0 / 106.5
 #   pallas / vesta: reference 82.8 / 109.5, 82.4 / 109.0 (window-5 with shared-memory slots: 88.0 / 115.9)
+#
+# Round 2: "searched" = a chain found by tools/chain_opt.py (dictionary-based sliding window with an annealed
+# dictionary, stored in tools/chains.json and re-verified here): fewer multiplies than the reference's chain AND 10-13
+# live values instead of 19-28, which keeps the slot file L2-resident (no local-memory write-back to HBM).
 CHAIN_SOURCE = {"pallas": "reference", "vesta": "reference", "bls12_381": "reference"}
+CHAIN_SOURCE.update({k: v for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_CHAIN_SOURCE", "").split(",") if kv)})
+CHAINS_JSON = os.environ.get("ANEMOI_CHAINS_JSON", os.path.join(ROOT, "tools", "chains.json"))
 
 
 def limbs(v, n, bits):
@@ -215,8 +221,13 @@ def main():
         first, ops = sliding_window(inv_alpha, w)
         nsq, nmul = check_schedule(inv_alpha, w, first, ops)
         table = 1 << (w - 1)
-        use_program = CHAIN_SOURCE.get(field, "window") == "reference"
-        if use_program:
+        use_program = CHAIN_SOURCE.get(field, "window") in ("reference", "searched")
+        if CHAIN_SOURCE.get(field, "window") == "searched":
+            with open(CHAINS_JSON) as cf:
+                rec = json.load(cf)[field]
+            prog, slots = [tuple(x) for x in rec["program"]], rec["slots"]
+            source = "searched chain (tools/chain_opt.py, dictionary %s)" % rec["dict"]
+        elif use_program:
             prog, slots = program_from_chain(fp["chain"])
             source = "reference chain (src/%s/sbox.rs)" % field
         else:
