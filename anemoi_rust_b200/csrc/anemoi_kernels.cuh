@@ -172,8 +172,17 @@ FPQ void sbox_column(uint32_t (&x)[F::N], uint32_t (&y)[F::N]) {
 
 // Anemoi::mds_layer (src/traits.rs:129-157) incl. the PHT. COLS = 1: local. COLS = 2: the two lanes of
 // a state exchange columns and both evaluate the (cheap) 2-column layer, keeping their own column.
+// The 2-column layer is a real function call, on purpose. ptxas balances integer adds between the ALU pipe (IADD3) and the
+// FMA pipe (IMAD.X / IMAD.IADD / IMAD.MOV) per FUNCTION: with this add-heavy layer inlined into the kernel it moves
+// 10-15 adds of every multiply / squaring in the hot loops onto the FMA-heavy pipe those loops saturate (SASS: +2-5 %
+// FMA-heavy cycles per squaring in every Anemoi-4-3 kernel). One call per round costs nothing measurable.
+#if defined(ANEMOI_INLINE_LINEAR)
+#define ANEMOI_LINEAR_Q FPQ
+#else
+#define ANEMOI_LINEAR_Q __device__ __noinline__
+#endif
 template <class F, int COLS>
-FPQ void linear_layer(uint32_t (&x)[F::N], uint32_t (&y)[F::N], int col, unsigned pair_mask) {
+ANEMOI_LINEAR_Q void linear_layer(uint32_t (&x)[F::N], uint32_t (&y)[F::N], int col, unsigned pair_mask) {
     constexpr int N = F::N;
     if (COLS == 1) {
         fp::add_mod<F>(y, y, x);
@@ -392,15 +401,6 @@ __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelA
     anemoi_body<F, COLS>(a);
 }
 
-#ifdef ANEMOI_LATENCY_KERNEL
-// Latency form for batches below one wave (upper Merkle levels, small API calls): one warp per block, no register cap,
-// so ptxas can schedule the multiply's independent carry chains further apart -- with a single warp per SM
-// sub-partition nothing else hides the dependent-issue latency.
-template <class F, int COLS>
-__global__ void __launch_bounds__(32, 1) anemoi_kernel_lat(KernelArgs a) {
-    anemoi_body<F, COLS>(a);
-}
-#endif
 
 // Diagnostic kernel: ONE layer of the round function on a batch of states, in place -- the reference exposes
 // ark_layer / mds_layer / sbox_layer / round as trait methods (src/traits.rs:113-157, 328-367); this lets each of

@@ -828,8 +828,8 @@ int anemoi_b200_merkle_root_sharded_dev(int field, int inst, int arity, const ui
     if (n_local == 0) return ANEMOI_B200_ERR_LENGTH;
     if (!d_local_leaves || !d_root) return ANEMOI_B200_ERR_ARG;
     int world = 1;
-    const anemoi::nccl::Api& nc = anemoi::nccl::api();
-    if (nccl_comm) {
+    if (nccl_comm) {  // NCCL is only bound (dlopen) when a communicator is actually in play
+        const anemoi::nccl::Api& nc = anemoi::nccl::api();
         if (!nc.ok) return nccl_fail(-1, "NCCL");
         NK(nc.CommCount((anemoi::nccl::comm_t)nccl_comm, &world));
     }
@@ -855,6 +855,7 @@ int anemoi_b200_merkle_root_sharded_dev(int field, int inst, int arity, const ui
     rc = anemoi_b200_merkle_reduce_dev(field, inst, arity, d_local_leaves, n_local, plan.local_levels, local_scratch, partial, st);
     if (rc) return rc;
     // the one exchange step of the path: <= 2 field elements (<= 96 bytes) per rank over NVLink
+    const anemoi::nccl::Api& nc = anemoi::nccl::api();
     NK(nc.AllGather(partial, gathered, plan.roots_per_rank * fb, anemoi::nccl::kUint8, (anemoi::nccl::comm_t)nccl_comm, st));
     return anemoi_b200_merkle_reduce_dev(field, inst, arity, gathered, plan.roots_per_rank * (size_t)world, plan.top_levels,
                                          top_scratch, d_root, st);

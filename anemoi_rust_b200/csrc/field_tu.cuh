@@ -38,10 +38,6 @@ static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     if (a.mode >= MODE_LAYER_ARK)
         anemoi_layer_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
-#ifdef ANEMOI_LATENCY_KERNEL
-    else if (block == 32)
-        anemoi_kernel_lat<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
-#endif
     else
         anemoi_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
     return cudaGetLastError();

@@ -68,6 +68,10 @@ FPQ void madc_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { emu_mad
 FPQ void madc_wide_cc_to(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
     emu_mad_pair(dlo, dhi, a, b, clo, chi, true, true);
 }
+// {lo,hi} = a*b + {lo or 0, hi or 0} [+ carry]; carry out. lo_zero / hi_zero: that accumulator word is known to be zero.
+FPQ void mac_pair(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, bool cin, bool lo_zero, bool hi_zero) {
+    emu_mad_pair(lo, hi, a, b, lo_zero ? 0u : lo, hi_zero ? 0u : hi, cin, true);
+}
 FPQ void add_cc(uint32_t& a, uint32_t b) { uint64_t t = (uint64_t)a + b; a = (uint32_t)t; g_cc = (uint32_t)(t >> 32); }
 FPQ void addc_cc(uint32_t& a, uint32_t b) { uint64_t t = (uint64_t)a + b + g_cc; a = (uint32_t)t; g_cc = (uint32_t)(t >> 32); }
 FPQ void addc(uint32_t& a, uint32_t b) { a = a + b + g_cc; }
@@ -98,6 +102,30 @@ FPQ void madc_wide_cc_to(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, u
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
                  : "=r"(dlo), "=r"(dhi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
 }
+// {lo,hi} = a*b + {lo or 0, hi or 0} [+ carry]; carry out. lo_zero / hi_zero (compile-time after unrolling): that
+// accumulator word is known to be zero -- the addend is then the immediate 0 and the word is a pure output, so no register
+// has to be zeroed first (ptxas does that with IMAD.MOV Rd, RZ, RZ, RZ on the FMA-heavy pipe).
+FPQ void mac_pair(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, bool cin, bool lo_zero, bool hi_zero) {
+    if (cin) {
+        if (lo_zero && hi_zero)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.cc.u32 %1, %2, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+        else if (lo_zero)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.cc.u32 %1, %2, %3, %1;" : "=r"(lo), "+r"(hi) : "r"(a), "r"(b));
+        else if (hi_zero)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, 0;" : "+r"(lo), "=r"(hi) : "r"(a), "r"(b));
+        else
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+    } else {
+        if (lo_zero && hi_zero)
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, 0; madc.hi.cc.u32 %1, %2, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+        else if (lo_zero)
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, 0; madc.hi.cc.u32 %1, %2, %3, %1;" : "=r"(lo), "+r"(hi) : "r"(a), "r"(b));
+        else if (hi_zero)
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, 0;" : "+r"(lo), "=r"(hi) : "r"(a), "r"(b));
+        else
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+    }
+}
 FPQ void add_cc(uint32_t& a, uint32_t b) { asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a) : "r"(b)); }
 FPQ void addc_cc(uint32_t& a, uint32_t b) { asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(a) : "r"(b)); }
 FPQ void addc(uint32_t& a, uint32_t b) { asm volatile("addc.u32 %0, %0, %1;" : "+r"(a) : "r"(b)); }
@@ -107,6 +135,31 @@ FPQ void subc(uint32_t& a, uint32_t b) { asm volatile("subc.u32 %0, %0, %1;" : "
 // funnel shift left: high 32 bits of ({hi,lo} << s), 0 < s < 32
 FPQ uint32_t shf_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 #endif
+
+// Carry fix-ups and the pipe they run on.
+// A row of multiply-accumulates ends with "top word += carry". Its own carry-out is zero (the accumulators never
+// overflow their top word), so the natural PTX is addc.u32 -- which ptxas lowers to IMAD.X Rd, RZ, RZ, Rd, P on the
+// FMA-heavy pipe, the one pipe this code saturates (it does the same to plain adds: IMAD.IADD, and to moves: IMAD.MOV;
+// an opaque zero or an explicit SEL + add do not help, measured in SASS). An add WITH a live carry-out, however, exists
+// only as IADD3.X on the ALU pipe. So with F::CARRY_CHAIN the fix-up is addc.cc and the (zero) carry it produces is consumed by
+// the first instruction of the NEXT carry chain (addc.cc / madc.lo.cc instead of add.cc / mad.lo.cc): no instruction is
+// added, the fix-ups move to the idle ALU pipe. The *_after_fixup forms mark exactly those chain starts.
+// The price is instruction-level parallelism: the next chain cannot start before the fix-up. Whether the trade pays is
+// measured per field (F::CARRY_CHAIN, tools/gen_params.py): ptxas emits the IMAD.X forms in the 8-limb kernels and in
+// bls12_377, not in bls12_381. (Also tried, in SASS: carry -> 0/1 register via SEL plus a three-input add -- ptxas splits
+// that into IMAD.IADD pairs; an opaque zero addend -- IMAD.X Rd, Rz, 0x1, Rd; addc.cc with a dead carry-out -- demoted.)
+template <class F>
+FPQ void fixup_carry(uint32_t& a) {
+    if (F::CARRY_CHAIN) addc_cc(a, 0u); else addc(a, 0u);
+}
+template <class F>
+FPQ void add_cc_after_fixup(uint32_t& a, uint32_t b) {
+    if (F::CARRY_CHAIN) addc_cc(a, b); else add_cc(a, b);
+}
+template <class F>
+FPQ void mad_wide_cc_after_fixup(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    if (F::CARRY_CHAIN) madc_wide_cc(lo, hi, a, b); else mad_wide_cc(lo, hi, a, b);
+}
 
 // ------------------------------------------------------------------------------------------------
 // modular add / sub / small multiples (canonical in, canonical out)
@@ -236,21 +289,31 @@ template <class F>
 struct ModRow {
     static constexpr int N = F::N;
     // {lo,hi} (+)= P*m [+ carry]; carry out. FIRST: no carry in. TO: write {dlo,dhi} = P*m + {clo,chi}.
-    template <bool FIRST>
+    // AFTER_FIXUP (with FIRST): this chain start directly follows a fixup_carry and consumes its zero carry.
+    template <bool FIRST, bool AFTER_FIXUP = false>
     static FPQ void mac(uint32_t& lo, uint32_t& hi, int j, uint32_t m) {
         const uint32_t P = F::p(j);
+        constexpr bool NOCIN = FIRST && !(AFTER_FIXUP && F::CARRY_CHAIN);
         if (F::special_limb(j) && P == 0) {
-            if (FIRST) add_cc(lo, 0u); else addc_cc(lo, 0u);
+            if (NOCIN) add_cc(lo, 0u); else addc_cc(lo, 0u);
             addc_cc(hi, 0u);
         } else if (F::special_limb(j) && P == 1) {
-            if (FIRST) add_cc(lo, m); else addc_cc(lo, m);
+            if (NOCIN) add_cc(lo, m); else addc_cc(lo, m);
             addc_cc(hi, 0u);
         } else if (F::special_limb(j) && fp_is_pow2(P)) {
             const int k = fp_log2(P);
-            if (FIRST) add_cc(lo, m << k); else addc_cc(lo, m << k);
+            if (NOCIN) add_cc(lo, m << k); else addc_cc(lo, m << k);
             addc_cc(hi, m >> (32 - k));
+        } else if (F::WIDE_P0 && FIRST && j == 0) {
+            // m * p[0] + t0 has a zero low word by construction, so ptxas turns the fused MAC into IMAD.HI.U32, which holds
+            // the FMA-heavy pipe 6 cycles against IMAD.WIDE's 4. Keep the product a plain IMAD.WIDE and do the accumulate
+            // on the ALU pipe (the low sum is dead but its carry is not, so the product's low word stays needed).
+            uint32_t l, h;
+            mul_wide(l, h, P, m);
+            if (NOCIN) add_cc(lo, l); else addc_cc(lo, l);
+            addc_cc(hi, h);
         } else {
-            if (FIRST) mad_wide_cc(lo, hi, P, m); else madc_wide_cc(lo, hi, P, m);
+            if (NOCIN) mad_wide_cc(lo, hi, P, m); else madc_wide_cc(lo, hi, P, m);
         }
     }
     static FPQ void mac_to(uint32_t& dlo, uint32_t& dhi, int j, uint32_t m, uint32_t clo, uint32_t chi) {
@@ -269,13 +332,15 @@ struct ModRow {
             madc_wide_cc_to(dlo, dhi, P, m, clo, chi);
         }
     }
+    template <bool AFTER_FIXUP = false>
     static FPQ void cmad_even(uint32_t* acc, uint32_t m) {
-        mac<true>(acc[0], acc[1], 0, m);
+        mac<true, AFTER_FIXUP>(acc[0], acc[1], 0, m);
         FP_UNROLL
         for (int j = 2; j < N; j += 2) mac<false>(acc[j], acc[j + 1], j, m);
     }
+    template <bool AFTER_FIXUP = false>
     static FPQ void cmad_odd(uint32_t* acc, uint32_t m) {
-        mac<true>(acc[0], acc[1], 1, m);
+        mac<true, AFTER_FIXUP>(acc[0], acc[1], 1, m);
         FP_UNROLL
         for (int j = 2; j < N; j += 2) mac<false>(acc[j], acc[j + 1], j + 1, m);
     }
@@ -300,16 +365,20 @@ FPQ void mad_redc_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t
         for (int j = 0; j < N; j += 2) mul_wide(odd[j], odd[j + 1], a[j + 1], bi);
         FP_UNROLL
         for (int j = 0; j < N; j += 2) mul_wide(even[j], even[j + 1], a[j], bi);
+        uint32_t m = F::quotient_digit(even[0]);
+        ModRow<F>::cmad_odd(odd, m);
+        ModRow<F>::cmad_even(even, m);
+        fixup_carry<F>(odd[N - 1]);
     } else {
-        add_cc(even[0], odd[1]);
+        add_cc_after_fixup<F>(even[0], odd[1]);  // every non-first row follows the previous row's closing fix-up
         madc_row_rshift<N>(odd, a + 1, bi);
         cmad_row<N>(even, a, bi);
-        addc(odd[N - 1], 0u);
+        fixup_carry<F>(odd[N - 1]);
+        uint32_t m = F::quotient_digit(even[0]);  // mul.lo / sub do not touch the carry flag
+        ModRow<F>::template cmad_odd<true>(odd, m);
+        ModRow<F>::cmad_even(even, m);
+        fixup_carry<F>(odd[N - 1]);
     }
-    uint32_t m = F::quotient_digit(even[0]);
-    ModRow<F>::cmad_odd(odd, m);
-    ModRow<F>::cmad_even(even, m);
-    addc(odd[N - 1], 0u);
 }
 
 // After an even number of rows the running value is T = odd + (even << 32) with odd[0] == 0 (the last
@@ -319,7 +388,7 @@ FPQ void merge_even_odd(uint32_t (&r)[F::N], const uint32_t* even, const uint32_
     constexpr int N = F::N;
     FP_UNROLL
     for (int j = 0; j < N; j++) r[j] = even[j];
-    add_cc(r[0], odd[1]);
+    add_cc_after_fixup<F>(r[0], odd[1]);  // follows the last row's closing fix-up
     FP_UNROLL
     for (int j = 1; j < N - 1; j++) addc_cc(r[j], odd[j + 1]);
     addc(r[N - 1], 0u);
@@ -348,13 +417,13 @@ FPQ void redc_row(uint32_t* even, uint32_t* odd, bool first) {
         uint32_t m = F::quotient_digit(even[0]);
         ModRow<F>::mul_odd(odd, m);
         ModRow<F>::cmad_even(even, m);
-        addc(odd[N - 1], 0u);
+        fixup_carry<F>(odd[N - 1]);
     } else {
-        add_cc(even[0], odd[1]);
+        add_cc_after_fixup<F>(even[0], odd[1]);  // follows the previous row's closing fix-up
         uint32_t m = F::quotient_digit(even[0]);  // mul.lo does not touch the carry flag
         ModRow<F>::madc_odd_rshift(odd, m);
         ModRow<F>::cmad_even(even, m);
-        addc(odd[N - 1], 0u);
+        fixup_carry<F>(odd[N - 1]);
     }
 }
 
@@ -366,35 +435,42 @@ FPQ void mont_sqr(uint32_t (&r)[F::N], const uint32_t (&a)[F::N]) {
     //   ev[k] : limb position k        (pairs (2t, 2t+1))
     //   od[k] : limb position k + 1    (pairs (2t+1, 2t+2))
     uint32_t ev[2 * N], od[2 * N];
+    bool tev[2 * N], tod[2 * N];  // word already written? (compile-time after unrolling, like every index below)
     FP_UNROLL
-    for (int k = 0; k < 2 * N; k++) { ev[k] = 0; od[k] = 0; }
+    for (int k = 0; k < 2 * N; k++) { ev[k] = 0; od[k] = 0; tev[k] = false; tod[k] = false; }
+    // `live` = the previous instruction of the carry-flag sequence was a fix-up whose (zero) carry the next chain start
+    // must consume (F::CARRY_CHAIN, see above). A product into two untouched words cannot carry out, so a chain that ENDS on one
+    // needs no fix-up, and one that STARTS on one (with nothing to consume) is a plain mul.wide.
+    bool live = false;
     FP_UNROLL
     for (int i = 0; i < N - 1; i++) {
-        // j = i+1, i+3, ... : position i+j odd -> od index i+j-1
-        {
-            bool open = false;
+        FP_UNROLL
+        for (int par = 0; par < 2; par++) {  // par 0: j = i+1, i+3, .. -> od[i+j-1];  par 1: j = i+2, i+4, .. -> ev[i+j]
+            uint32_t* acc = par ? ev : od;
+            bool* touched = par ? tev : tod;
+            bool cin = live && F::CARRY_CHAIN;  // carry flag holds something the next instruction must take in
+            bool pending = false;          // ... and it may be non-zero
+            bool any = false;
             int top = 0;
             FP_UNROLL
-            for (int j = i + 1; j < N; j += 2) {
-                int k = i + j - 1;
-                if (!open) { mad_wide_cc(od[k], od[k + 1], a[i], a[j]); open = true; }
-                else madc_wide_cc(od[k], od[k + 1], a[i], a[j]);
+            for (int j = i + 1 + par; j < N; j += 2) {
+                const int k = par ? i + j : i + j - 1;
+                const bool fresh = !touched[k] && !touched[k + 1];
+                if (fresh && !cin) {
+                    mul_wide(acc[k], acc[k + 1], a[i], a[j]);
+                } else {
+                    mac_pair(acc[k], acc[k + 1], a[i], a[j], cin, !touched[k], !touched[k + 1]);
+                    cin = true;
+                    pending = !fresh;
+                }
+                touched[k] = true; touched[k + 1] = true;
+                any = true;
                 top = k + 2;
             }
-            if (open && top < 2 * N) addc(od[top], 0u);
-        }
-        // j = i+2, i+4, ... : position i+j even -> ev index i+j
-        {
-            bool open = false;
-            int top = 0;
-            FP_UNROLL
-            for (int j = i + 2; j < N; j += 2) {
-                int k = i + j;
-                if (!open) { mad_wide_cc(ev[k], ev[k + 1], a[i], a[j]); open = true; }
-                else madc_wide_cc(ev[k], ev[k + 1], a[i], a[j]);
-                top = k + 2;
+            if (any) {
+                if (pending && top < 2 * N) { fixup_carry<F>(acc[top]); touched[top] = true; live = true; }
+                else live = false;
             }
-            if (open && top < 2 * N) addc(ev[top], 0u);
         }
     }
     // ---- w = ev + (od << 32)
@@ -402,16 +478,18 @@ FPQ void mont_sqr(uint32_t (&r)[F::N], const uint32_t (&a)[F::N]) {
     w[0] = ev[0];
     FP_UNROLL
     for (int k = 1; k < 2 * N; k++) w[k] = ev[k];
-    add_cc(w[1], od[0]);
+    if (live) add_cc_after_fixup<F>(w[1], od[0]);
+    else add_cc(w[1], od[0]);
     FP_UNROLL
     for (int k = 2; k < 2 * N - 1; k++) addc_cc(w[k], od[k - 1]);
-    addc(w[2 * N - 1], od[2 * N - 2]);
+    // the cross-product sum is below 2^(64N-1): no carry out of the top word, which is what lets this add act as a fix-up
+    if (F::CARRY_CHAIN) addc_cc(w[2 * N - 1], od[2 * N - 2]); else addc(w[2 * N - 1], od[2 * N - 2]);
     // ---- w = 2w (funnel shifts; the top bit is clear because 2*cross < a^2 < 2^(64N))
     FP_UNROLL
     for (int k = 2 * N - 1; k >= 1; k--) w[k] = shf_l(w[k - 1], w[k], 1);
     w[0] = w[0] << 1;
-    // ---- w += sum_i a_i^2 2^(64 i)
-    mad_wide_cc(w[0], w[1], a[0], a[0]);
+    // ---- w += sum_i a_i^2 2^(64 i)   (shifts do not touch the carry flag: this chain consumes the zero carry above)
+    mad_wide_cc_after_fixup<F>(w[0], w[1], a[0], a[0]);
     FP_UNROLL
     for (int i = 1; i < N - 1; i++) madc_wide_cc(w[2 * i], w[2 * i + 1], a[i], a[i]);
     madc_wide(w[2 * N - 2], w[2 * N - 1], a[N - 1], a[N - 1]);
@@ -426,12 +504,12 @@ FPQ void mont_sqr(uint32_t (&r)[F::N], const uint32_t (&a)[F::N]) {
     uint32_t u[N];
     FP_UNROLL
     for (int j = 0; j < N; j++) u[j] = w[j];
-    add_cc(u[0], odd[1]);
+    add_cc_after_fixup<F>(u[0], odd[1]);  // follows the last row's closing fix-up
     FP_UNROLL
     for (int j = 1; j < N - 1; j++) addc_cc(u[j], odd[j + 1]);
-    addc(u[N - 1], 0u);
+    fixup_carry<F>(u[N - 1]);
     // + high half
-    add_cc(u[0], w[N]);
+    add_cc_after_fixup<F>(u[0], w[N]);
     FP_UNROLL
     for (int j = 1; j < N - 1; j++) addc_cc(u[j], w[N + j]);
     addc(u[N - 1], w[2 * N - 1]);

@@ -13,6 +13,7 @@
 //   5  DFMA
 //   6  variant 2 + one DFMA per IMAD.WIDE    (MAC32 counted; do FP64 and integer multiply overlap?)
 //   7  variant 2 + one IMAD per IMAD.WIDE    (MAC32 counted)
+//   8  heterogeneous warps: half the warps IMAD.WIDE only, half DFMA only (ops of both kinds counted together)
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -171,6 +172,44 @@ __global__ void __launch_bounds__(kThreads) k_dfma(uint32_t* out, const uint32_t
     if (acc == 0.12345678) out[threadIdx.x] = (uint32_t)acc;
 }
 
+// Heterogeneous warps: even warps run only IMAD.WIDE, odd warps only DFMA (16 independent accumulators each), so that
+// neither instruction stream waits on the other inside a warp. If the FP64 pipe and the integer-multiply (FMA-heavy)
+// pipe were independent, the two halves would each run at their stand-alone rate; if they share an issue port the
+// SUM of port-cycles stays at 100 %. Counted: 16 ops per iteration per thread, whatever the flavour.
+__global__ void __launch_bounds__(kThreads) k_hetero(uint32_t* out, const uint32_t* in, long long* cycles) {
+    LOAD_INPUTS();
+    unsigned long long q[16];
+    double d[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        q[i] = in[64 + i];
+        d[i] = (double)in[96 + i];
+    }
+    const double da = (double)a * 1e-9, db = (double)b[0] * 1e-9;
+    const bool fp = (threadIdx.x >> 5) & 1;
+    Probe p;
+    p.start();
+    if (fp) {
+#pragma unroll 1
+        for (int it = 0; it < kIters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(da), "d"(db));
+        }
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < kIters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) q[i] = (unsigned long long)a * b[i] + q[i];
+            a += 0x9e3779b9u;
+        }
+    }
+    p.stop(cycles);
+    unsigned long long acc = a;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= q[i] ^ (unsigned long long)d[i];
+    if (acc == 0x12345678u) out[threadIdx.x] = (uint32_t)acc;
+}
+
 typedef void (*kernel_t)(uint32_t*, const uint32_t*, long long*);
 
 int run_variant(kernel_t kernel, double* ops_per_s, double* sm_mhz) {
@@ -226,6 +265,7 @@ extern "C" int anemoi_b200_imad_peak(int variant, double* ops_per_s, double* sm_
         case 5: return run_variant(k_dfma, ops_per_s, sm_mhz);
         case 6: return run_variant(k_imad_wide<2>, ops_per_s, sm_mhz);
         case 7: return run_variant(k_imad_wide<3>, ops_per_s, sm_mhz);
+        case 8: return run_variant(k_hetero, ops_per_s, sm_mhz);
         default: return ANEMOI_B200_ERR_ARG;
     }
 }

@@ -322,6 +322,13 @@ class _AnemoiBase:
         f = cls.FIELD
         a = _np_in(leaves, f.n64)
         out = np.empty((1, f.n64), dtype=np.uint64)
+        if n_gpus > 1:
+            # the library binds NCCL at run time and reuses a copy the process already mapped: make sure that copy is
+            # PyTorch's (when there is one) rather than the system's, or a later `import torch` would trip over it
+            try:
+                import torch  # noqa: F401
+            except ImportError:
+                pass
         ffi.check(_lib.anemoi_b200_merkle_root(f.id, cls.INST, cls.STATE_WIDTH, _ptr(a), a.size // f.n64, _ptr(out),
                                                n_gpus))
         return out

@@ -218,9 +218,11 @@ int anemoi_b200_merkle_verify(int field, int inst, int arity, const uint64_t* le
 
 /* ---- roofline denominator ------------------------------------------------------------------ */
 /* Chip-wide issue rate of one integer-multiply flavour on the current device, measured with
- * independent chains. variant: 0 mad.lo.u32, 1 mad.hi.u32, 2 mad.wide.u32, 3 carry-chained
- * mad.lo.cc/madc.hi.cc pairs (= IMAD.WIDE.U32.X, what the kernels issue), 4 = 3 with co-issued IADD3,
- * 5 fma.rn.f64 (context). ops_per_s = instructions (MAC32 for 2-4) per second; sm_mhz = SM clock seen. */
+ * independent chains. variant: 0 mad.lo.u32, 1 mad.hi.u32, 2 mad.wide.u32 (the roofline peak), 3 carry-chained
+ * mad.lo.cc/madc.hi.cc pairs (= IMAD.WIDE.U32.X, what the kernels issue), 4 = 2 + one add.u32 per multiply,
+ * 5 fma.rn.f64, 6 = 2 + one DFMA per multiply, 7 = 2 + one IMAD per multiply, 8 = half the warps IMAD.WIDE only and
+ * half DFMA only (6-8: do the FP64 and integer-multiply pipes overlap? -- DESIGN.md 3.3).
+ * ops_per_s = instructions (MAC32 for 2-4, 6, 7) per second; sm_mhz = SM clock seen. */
 int anemoi_b200_imad_peak(int variant, double* ops_per_s, double* sm_mhz);
 
 #ifdef __cplusplus

@@ -25,6 +25,14 @@ static int run(int op, const uint32_t* a_, const uint32_t* b_, uint32_t* r_) {
     return 0;
 }
 
+// The per-field code-generation switches (F::CARRY_CHAIN, F::WIDE_P0: tools/gen_params.py) change which PTX sequences
+// run, not the result. `variant` 1 flips both so that every field is checked on both paths.
+template <class F>
+struct Flipped : F {
+    static constexpr bool CARRY_CHAIN = !F::CARRY_CHAIN;
+    static constexpr bool WIDE_P0 = !F::WIDE_P0;
+};
+
 extern "C" int fp_emu_limbs(int field) {
     switch (field) {
         case 0: return F_bls12_377::N;
@@ -34,6 +42,19 @@ extern "C" int fp_emu_limbs(int field) {
         case 4: return F_jubjub::N;
         case 5: return F_pallas::N;
         case 6: return F_vesta::N;
+    }
+    return -1;
+}
+
+extern "C" int fp_emu_op_flipped(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    switch (field) {
+        case 0: return run<Flipped<F_bls12_377>>(op, a, b, r);
+        case 1: return run<Flipped<F_bls12_381>>(op, a, b, r);
+        case 2: return run<Flipped<F_bn_254>>(op, a, b, r);
+        case 3: return run<Flipped<F_ed_on_bls12_377>>(op, a, b, r);
+        case 4: return run<Flipped<F_jubjub>>(op, a, b, r);
+        case 5: return run<Flipped<F_pallas>>(op, a, b, r);
+        case 6: return run<Flipped<F_vesta>>(op, a, b, r);
     }
     return -1;
 }

@@ -20,6 +20,7 @@ def emu(tmp_path_factory):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(out), src])
     lib = ctypes.CDLL(str(out))
     lib.fp_emu_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.fp_emu_op_flipped.argtypes = lib.fp_emu_op.argtypes
     return lib
 
 
@@ -28,7 +29,13 @@ def call(lib, fi, op, n, a, b=0):
     B = (ctypes.c_uint32 * n)(*[(b >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
     Rr = (ctypes.c_uint32 * n)()
     assert lib.fp_emu_op(fi, op, A, B, Rr) == 0
-    return sum(int(Rr[i]) << (32 * i) for i in range(n))
+    res = sum(int(Rr[i]) << (32 * i) for i in range(n))
+    # the same operation with the per-field code-generation switches (carry-chained fix-ups, IMAD.WIDE for m * p[0])
+    # flipped must give the identical limbs: both paths are live, chosen per field by measurement
+    R2 = (ctypes.c_uint32 * n)()
+    assert lib.fp_emu_op_flipped(fi, op, A, B, R2) == 0
+    assert list(R2) == list(Rr), "carry-chain / wide-p0 paths disagree"
+    return res
 
 
 @pytest.mark.parametrize("field", R.FIELDS)

@@ -31,6 +31,18 @@ WINDOW = {"bls12_377": 5, "bls12_381": 5, "bn_254": 4, "ed_on_bls12_377": 5, "ju
 SPECIAL_LIMBS = {
     "bls12_377": [0], "ed_on_bls12_377": [0], "jubjub": [0], "pallas": [0], "vesta": [0],
 }
+# Per-field code-generation switches of fp.cuh, chosen by measurement on B200 (ptxas' ALU-vs-FMA balancing differs from
+# kernel to kernel, see fp.cuh): CARRY_CHAIN = the end-of-row carry fix-ups keep their (zero) carry-out alive so that they
+# stay IADD3.X on the ALU pipe (helps where ptxas would otherwise emit IMAD.X on the saturated FMA-heavy pipe; costs
+# instruction-level parallelism where it would not); WIDE_P0 = m * p[0] as IMAD.WIDE + ALU accumulate instead of the
+# 6-cycle IMAD.HI ptxas makes of the fused form (only meaningful when p[0] is not a special limb).
+CARRY_CHAIN = {"bls12_377": 1, "bls12_381": 0, "bn_254": 0, "ed_on_bls12_377": 1, "jubjub": 0, "pallas": 1, "vesta": 1}
+WIDE_P0 = {"bls12_381": 0, "bn_254": 0}
+for _name, _tbl in (("ANEMOI_CARRY_CHAIN", CARRY_CHAIN), ("ANEMOI_WIDE_P0", WIDE_P0)):
+    _tbl.update({k: int(v) for k, v in (kv.split("=") for kv in os.environ.get(_name, "").split(",") if kv)})
+# developer override for A/B runs: ANEMOI_SPECIAL_LIMBS="pallas=0:4:5,vesta=0:4:5"
+SPECIAL_LIMBS.update({k: [int(x) for x in v.split(":") if x != ""] for k, v in
+                      (kv.split("=") for kv in os.environ.get("ANEMOI_SPECIAL_LIMBS", "").split(",") if kv)})
 
 
 # which exponentiation program each field runs: "window" = sliding window of WINDOW[field] bits (specialised code
@@ -43,7 +55,8 @@ SPECIAL_LIMBS = {
 # Round 2: "searched" = a chain found by tools/chain_opt.py (dictionary-based sliding window with an annealed
 # dictionary, stored in tools/chains.json and re-verified here): fewer multiplies than the reference's chain AND 10-13
 # live values instead of 19-28, which keeps the slot file L2-resident (no local-memory write-back to HBM).
-CHAIN_SOURCE = {"pallas": "reference", "vesta": "reference", "bls12_381": "reference"}
+CHAIN_SOURCE = {"bls12_377": "searched", "bls12_381": "searched", "bn_254": "searched", "ed_on_bls12_377": "searched",
+                "jubjub": "searched", "pallas": "searched", "vesta": "reference"}
 CHAIN_SOURCE.update({k: v for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_CHAIN_SOURCE", "").split(",") if kv)})
 CHAINS_JSON = os.environ.get("ANEMOI_CHAINS_JSON", os.path.join(ROOT, "tools", "chains.json"))
 
@@ -271,6 +284,8 @@ def main():
         minb = 7 if n32 == 8 else 5
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
+        cu.append("    static constexpr bool CARRY_CHAIN = %s;  // fp.cuh: carry fix-ups chained through the carry flag\n" % ("true" if CARRY_CHAIN.get(field, 0) else "false"))
+        cu.append("    static constexpr bool WIDE_P0 = %s;      // fp.cuh: m * p[0] as IMAD.WIDE + ALU adds\n" % ("true" if WIDE_P0.get(field, 0) else "false"))
         cu.append("    static constexpr int SLOTS = %d;     // local-memory slots of the ladder (slot 0 = x)\n" % slots)
         cu.append("    // x^(1/alpha): %s, %d squarings + %d multiplies (reference chain: %d)\n" % (source, psq, pmul, len(fp["chain"])))
         cu.append("    static constexpr bool USE_PROGRAM = %s;\n" % ("true" if use_program else "false"))
@@ -280,6 +295,9 @@ def main():
         # Montgomery quotient digit m = t0 * n0inv. When n0inv = -1 it is a negation, done on the ALU pipe as
         # (opaque zero) - t0 so that ptxas neither spends an IMAD on it nor learns that m = -t0 (see above).
         cu.append("    HD static uint32_t quotient_digit(uint32_t t0) {\n#if defined(__CUDA_ARCH__) && defined(ANEMOI_FIELD_TABLES_%s)\n        return %s;\n#else\n        return t0 * N0INV;\n#endif\n    }\n" % (field, ("k_zero_%s - t0" % field) if n0inv32 == 0xFFFFFFFF else ("t0 * k_n0inv_%s" % field)))
+        # a zero that ptxas cannot see through (constant-memory load): used where a literal 0 would invite ptxas to move
+        # the instruction onto the saturated FMA-heavy pipe (IMAD.X Rd, RZ, RZ, Rd / IMAD.MOV Rd, RZ) -- see fp.cuh
+        cu.append("    HD static uint32_t opaque_zero() {\n#if defined(__CUDA_ARCH__) && defined(ANEMOI_FIELD_TABLES_%s)\n        return k_zero_%s;\n#else\n        return 0u;\n#endif\n    }\n" % (field, field))
         cu.append(switch_fn("p", limbs(p, n32, 32)))
         sp = SPECIAL_LIMBS.get(field, [])
         cu.append("    // modulus limbs whose m*p[j] product is done with adds/shifts on the ALU pipe (see fp.cuh ModRow)\n")
