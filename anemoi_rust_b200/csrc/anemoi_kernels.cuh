@@ -394,13 +394,32 @@ FPQ void anemoi_body(const KernelArgs& a) {
     }
 }
 
+// F with the code-generation switches of ONE kernel instantiation (see fp.cuh "Carry fix-ups" and tools/gen_params.py:
+// CARRY_CHAIN is measured per field AND per instantiation, because ptxas balances the pipes per kernel). LATENCY selects
+// the form for batches below a wave: never chained, since with a single warp per SM sub-partition nothing else hides the
+// serialisation the chained fix-ups introduce (measured: Pallas 4-3 1.49 vs 1.90 ms, BLS12-377 2-1 6.83 vs 8.49 ms per
+// lone launch).
+template <class F, int COLS, bool LATENCY>
+struct Variant : F {
+    static constexpr bool CARRY_CHAIN = !LATENCY && (COLS == 1 ? F::CARRY_CHAIN_2_1 : F::CARRY_CHAIN_4_3);
+};
+template <class F, int COLS, bool LATENCY>
+struct Tables<Variant<F, COLS, LATENCY>> : Tables<F> {};
+
 // Throughput form: F::BLOCK-thread blocks, F::MIN_BLOCKS resident per SM (register-capped so that the FMA-heavy pipe
 // always has 16+ warps to draw from).
 template <class F, int COLS>
 __global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelArgs a) {
-    anemoi_body<F, COLS>(a);
+    anemoi_body<Variant<F, COLS, false>, COLS>(a);
 }
 
+// Latency form, launched when the batch gives at most two warps per SM sub-partition (upper Merkle levels, small API
+// calls): one warp per block so the few warps spread over all SMs, no register cap, unchained carries. Only instantiated
+// where it differs from the throughput form.
+template <class F, int COLS>
+__global__ void __launch_bounds__(32, 1) anemoi_kernel_lat(KernelArgs a) {
+    anemoi_body<Variant<F, COLS, true>, COLS>(a);
+}
 
 // Diagnostic kernel: ONE layer of the round function on a batch of states, in place -- the reference exposes
 // ark_layer / mds_layer / sbox_layer / round as trait methods (src/traits.rs:113-157, 328-367); this lets each of

@@ -30,16 +30,20 @@ template <class F, int COLS>
 static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     if (a.n == 0) return cudaSuccess;
     const unsigned long long threads = a.n * COLS;
-    // Big batches: F::BLOCK-thread blocks, F::MIN_BLOCKS resident per SM. Small batches (upper Merkle levels,
-    // KATs): one warp per block so the few warps spread over all SMs.
+    // Big batches: F::BLOCK-thread blocks, F::MIN_BLOCKS resident per SM. Small batches (upper Merkle levels, KATs): one
+    // warp per block so the few warps spread over all SMs; at <= 2 warps per SM sub-partition the latency form runs.
     const int sms = cached_sm_count();
     const int block = (threads >= (unsigned long long)sms * F::BLOCK * 2) ? F::BLOCK : 32;
     const unsigned long long blocks = (threads + block - 1) / block;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
-    if (a.mode >= MODE_LAYER_ARK)
+    constexpr bool kHasLatencyForm = (COLS == 1 ? F::CARRY_CHAIN_2_1 : F::CARRY_CHAIN_4_3);
+    if (a.mode >= MODE_LAYER_ARK) {
         anemoi_layer_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
-    else
+    } else if (kHasLatencyForm && block == 32 && blocks <= (unsigned long long)sms * 8) {
+        if constexpr (kHasLatencyForm) anemoi_kernel_lat<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
+    } else {
         anemoi_kernel<F, COLS><<<(unsigned)blocks, block, 0, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -25,12 +25,11 @@ static int run(int op, const uint32_t* a_, const uint32_t* b_, uint32_t* r_) {
     return 0;
 }
 
-// The per-field code-generation switches (F::CARRY_CHAIN, F::WIDE_P0: tools/gen_params.py) change which PTX sequences
-// run, not the result. `variant` 1 flips both so that every field is checked on both paths.
+// The per-kernel code-generation switch F::CARRY_CHAIN (tools/gen_params.py) changes which PTX sequences run, not the
+// result. fp_emu_op_flipped runs the other setting so that every field is checked on both paths.
 template <class F>
 struct Flipped : F {
     static constexpr bool CARRY_CHAIN = !F::CARRY_CHAIN;
-    static constexpr bool WIDE_P0 = !F::WIDE_P0;
 };
 
 extern "C" int fp_emu_limbs(int field) {

@@ -30,11 +30,11 @@ def call(lib, fi, op, n, a, b=0):
     Rr = (ctypes.c_uint32 * n)()
     assert lib.fp_emu_op(fi, op, A, B, Rr) == 0
     res = sum(int(Rr[i]) << (32 * i) for i in range(n))
-    # the same operation with the per-field code-generation switches (carry-chained fix-ups, IMAD.WIDE for m * p[0])
-    # flipped must give the identical limbs: both paths are live, chosen per field by measurement
+    # the same operation with the code-generation switch (carry-chained fix-ups) flipped must give the identical limbs:
+    # both paths are live, chosen per kernel by measurement
     R2 = (ctypes.c_uint32 * n)()
     assert lib.fp_emu_op_flipped(fi, op, A, B, R2) == 0
-    assert list(R2) == list(Rr), "carry-chain / wide-p0 paths disagree"
+    assert list(R2) == list(Rr), "chained / unchained carry paths disagree"
     return res
 
 

@@ -34,12 +34,14 @@ SPECIAL_LIMBS = {
 # Per-field code-generation switches of fp.cuh, chosen by measurement on B200 (ptxas' ALU-vs-FMA balancing differs from
 # kernel to kernel, see fp.cuh): CARRY_CHAIN = the end-of-row carry fix-ups keep their (zero) carry-out alive so that they
 # stay IADD3.X on the ALU pipe (helps where ptxas would otherwise emit IMAD.X on the saturated FMA-heavy pipe; costs
-# instruction-level parallelism where it would not); WIDE_P0 = m * p[0] as IMAD.WIDE + ALU accumulate instead of the
-# 6-cycle IMAD.HI ptxas makes of the fused form (only meaningful when p[0] is not a special limb).
-CARRY_CHAIN = {"bls12_377": 1, "bls12_381": 0, "bn_254": 0, "ed_on_bls12_377": 1, "jubjub": 0, "pallas": 1, "vesta": 1}
-WIDE_P0 = {"bls12_381": 0, "bn_254": 0}
-for _name, _tbl in (("ANEMOI_CARRY_CHAIN", CARRY_CHAIN), ("ANEMOI_WIDE_P0", WIDE_P0)):
-    _tbl.update({k: int(v) for k, v in (kv.split("=") for kv in os.environ.get(_name, "").split(",") if kv)})
+# instruction-level parallelism where it would not).
+# (Anemoi-2-1 kernel, Anemoi-4-3 kernel); batches below a wave always run unchained (the latency form, anemoi_kernels.cuh)
+# Measured (ms per 2^20 states, chained / unchained, 2-1 and 4-3): bls12_377 262.9 / 262.4, 345.9 / 353.0; bls12_381 279.9 /
+# 272.3, 370.3 / 363.2; bn_254 88.5 / 87.7, 116.4 / 117.0; ed_on_bls12_377 74.1 / 76.0, 100.5 / 102.1; jubjub 85.2 / 84.8,
+# 112.8 / 111.5; pallas 79.7 / 80.8, 104.8 / 106.5; vesta 79.8 / 81.0, 105.0 / 106.8.
+CARRY_CHAIN = {"bls12_377": "01", "bls12_381": "00", "bn_254": "01", "ed_on_bls12_377": "11", "jubjub": "00", "pallas": "11",
+               "vesta": "11"}
+CARRY_CHAIN.update({k: v for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_CARRY_CHAIN", "").split(",") if kv)})
 # developer override for A/B runs: ANEMOI_SPECIAL_LIMBS="pallas=0:4:5,vesta=0:4:5"
 SPECIAL_LIMBS.update({k: [int(x) for x in v.split(":") if x != ""] for k, v in
                       (kv.split("=") for kv in os.environ.get("ANEMOI_SPECIAL_LIMBS", "").split(",") if kv)})
@@ -284,8 +286,11 @@ def main():
         minb = 7 if n32 == 8 else 5
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
-        cu.append("    static constexpr bool CARRY_CHAIN = %s;  // fp.cuh: carry fix-ups chained through the carry flag\n" % ("true" if CARRY_CHAIN.get(field, 0) else "false"))
-        cu.append("    static constexpr bool WIDE_P0 = %s;      // fp.cuh: m * p[0] as IMAD.WIDE + ALU adds\n" % ("true" if WIDE_P0.get(field, 0) else "false"))
+        cc = CARRY_CHAIN.get(field, "00")
+        cu.append("    // fp.cuh: carry fix-ups chained through the carry flag, per kernel instantiation (CARRY_CHAIN itself is what a\n    // bare F gets: the diagnostic layer kernel and the host emulation)\n")
+        cu.append("    static constexpr bool CARRY_CHAIN_2_1 = %s;\n" % ("true" if cc[0] == "1" else "false"))
+        cu.append("    static constexpr bool CARRY_CHAIN_4_3 = %s;\n" % ("true" if cc[1] == "1" else "false"))
+        cu.append("    static constexpr bool CARRY_CHAIN = CARRY_CHAIN_2_1;\n")
         cu.append("    static constexpr int SLOTS = %d;     // local-memory slots of the ladder (slot 0 = x)\n" % slots)
         cu.append("    // x^(1/alpha): %s, %d squarings + %d multiplies (reference chain: %d)\n" % (source, psq, pmul, len(fp["chain"])))
         cu.append("    static constexpr bool USE_PROGRAM = %s;\n" % ("true" if use_program else "false"))
