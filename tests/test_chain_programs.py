@@ -1,0 +1,111 @@
+"""The ladder programs compiled into the CUDA engine (anemoi_rust_b200/csrc/generated/fields.cuh: k_prog_<field>) are
+checked on the CPU: each is executed on exponents and must produce INV_ALPHA of the reference (src/<field>/sbox.rs:
+ALPHA * INV_ALPHA = 1 mod p - 1), stay inside its slot file, and -- executed on field elements with Python big integers --
+give x^(1/alpha), i.e. alpha-th power back to x. The searched chains (tools/chains.json) must also never be worse than the
+reference's own chain in the cost model the GPU pays (squarings and multiplies weighted by their MAC32 counts)."""
+import json
+import os
+import random
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PARAMS = json.load(open(os.path.join(ROOT, "tests", "golden", "params.json")))
+HEADER = open(os.path.join(ROOT, "anemoi_rust_b200", "csrc", "generated", "fields.cuh")).read()
+
+
+def struct_of(field):
+    m = re.search(r"struct F_%s \{(.*?)\n\};" % field, HEADER, flags=re.S)
+    return m.group(1)
+
+
+def const(field, name):
+    m = re.search(r"static constexpr \w+ %s = ([\w]+);" % name, struct_of(field))
+    v = m.group(1)
+    return {"true": True, "false": False}.get(v, None) if v in ("true", "false") else int(v)
+
+
+def program(field):
+    m = re.search(r"k_prog_%s\[(\d+)\]\[2\] = \{(.*?)\};" % field, HEADER, flags=re.S)
+    pairs = re.findall(r"\{(\d+),(\d+)\}", m.group(2))
+    assert len(pairs) == int(m.group(1))
+    return [(int(a), int(b)) for a, b in pairs]
+
+
+def run_accumulator_machine(prog, slots, one, mul, sqr):
+    """ISA of anemoi_kernels.cuh pow_program: 0 SQR n, 1 MUL slot, 2 LD slot, 3 ST slot; slot 0 = x, acc starts as x."""
+    T = [None] * slots
+    T[0] = one
+    acc = one
+    nsq = nmul = 0
+    for op, arg in prog:
+        if op == 0:
+            for _ in range(arg):
+                acc = sqr(acc)
+            nsq += arg
+        elif op == 1:
+            assert T[arg] is not None, "MUL from an empty slot"
+            acc = mul(acc, T[arg])
+            nmul += 1
+        elif op == 2:
+            assert T[arg] is not None, "LD from an empty slot"
+            acc = T[arg]
+        else:
+            assert 0 <= arg < slots
+            T[arg] = acc
+    return acc, nsq, nmul
+
+
+def run_window_schedule(field, sched, one, mul, sqr):
+    """The specialised sliding-window path (pow_window): T[k] = x^(2k+1), then {squarings, table index or 255} steps."""
+    slots = const(field, "SLOTS")
+    x2 = sqr(one)
+    T = [one]
+    for _ in range(1, slots):
+        T.append(mul(T[-1], x2))
+    acc = T[const(field, "SCHED_FIRST")]
+    for nsq, idx in sched:
+        for _ in range(nsq):
+            acc = sqr(acc)
+        if idx != 255:
+            acc = mul(acc, T[idx])
+    return acc
+
+
+@pytest.mark.parametrize("field", sorted(PARAMS))
+def test_generated_ladder_computes_inv_alpha(field):
+    fp = PARAMS[field]
+    p, e, alpha = int(fp["modulus"]), int(fp["inv_alpha"]), fp["alpha"]
+    assert alpha * e % (p - 1) == 1
+    prog = program(field)
+    if const(field, "USE_PROGRAM"):
+        assert len(prog) == const(field, "PROG_LEN")
+        got, nsq, nmul = run_accumulator_machine(prog, const(field, "SLOTS"), 1, lambda a, b: a + b, lambda a: 2 * a)
+        assert got == e
+        # on field elements: (x^(1/alpha))^alpha == x
+        rng = random.Random(5)
+        for _ in range(3):
+            x = rng.randrange(1, p)
+            y, _, _ = run_accumulator_machine(prog, const(field, "SLOTS"), x, lambda a, b: a * b % p, lambda a: a * a % p)
+            assert pow(y, alpha, p) == x
+        # cost the GPU pays (MAC32, squaring-aware) is not above the reference chain's
+        n = 2 * fp["n64"]
+        cs, cm = n * (n + 1) // 2 + n * n + n, 2 * n * n + n
+        ref_s = sum(1 for a, b in fp["chain"] if a == b)
+        ref_m = len(fp["chain"]) - ref_s
+        assert cs * nsq + cm * nmul <= cs * ref_s + cm * ref_m
+        assert const(field, "SLOTS") <= 16, "slot file must stay small enough to be L2-resident"
+    else:
+        assert len(prog) == const(field, "SCHED_LEN")
+        assert run_window_schedule(field, prog, 1, lambda a, b: a + b, lambda a: 2 * a) == e
+
+
+def test_chains_json_matches_generated_header():
+    """tools/chains.json (the committed output of tools/chain_opt.py) is what the header was generated from."""
+    table = json.load(open(os.path.join(ROOT, "tools", "chains.json")))
+    for field, rec in table.items():
+        if "searched chain" not in struct_of(field):
+            continue
+        assert [tuple(x) for x in rec["program"]] == program(field)
+        assert rec["slots"] == const(field, "SLOTS")

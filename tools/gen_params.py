@@ -42,6 +42,9 @@ SPECIAL_LIMBS = {
 CARRY_CHAIN = {"bls12_377": "01", "bls12_381": "00", "bn_254": "01", "ed_on_bls12_377": "11", "jubjub": "00", "pallas": "11",
                "vesta": "11"}
 CARRY_CHAIN.update({k: v for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_CARRY_CHAIN", "").split(",") if kv)})
+# Montgomery quotient digit m = t0 * (-p^-1 mod 2^32) by shift-adds where the constant allows it (bls12_381: -0x30003)
+QUOTIENT_SHIFT_ADD = {"bls12_381": 0}
+QUOTIENT_SHIFT_ADD.update({k: int(v) for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_QUOTIENT_SHIFT_ADD", "").split(",") if kv)})
 # developer override for A/B runs: ANEMOI_SPECIAL_LIMBS="pallas=0:4:5,vesta=0:4:5"
 SPECIAL_LIMBS.update({k: [int(x) for x in v.split(":") if x != ""] for k, v in
                       (kv.split("=") for kv in os.environ.get("ANEMOI_SPECIAL_LIMBS", "").split(",") if kv)})
@@ -283,7 +286,7 @@ def main():
         # (<= 96 registers, no spills); N = 8: 128 x 7 = 28 warps/SM (<= 72 registers, no spills). One block fewer
         # measured 0-1.5 % slower.
         blk = 128
-        minb = 7 if n32 == 8 else 5
+        minb = int(os.environ.get("ANEMOI_MIN_BLOCKS_%d" % n32, 7 if n32 == 8 else 5))
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
         cc = CARRY_CHAIN.get(field, "00")
@@ -299,7 +302,14 @@ def main():
         cu.append("    static constexpr int SCHED_LEN = %d;\n" % len(ops))
         # Montgomery quotient digit m = t0 * n0inv. When n0inv = -1 it is a negation, done on the ALU pipe as
         # (opaque zero) - t0 so that ptxas neither spends an IMAD on it nor learns that m = -t0 (see above).
-        cu.append("    HD static uint32_t quotient_digit(uint32_t t0) {\n#if defined(__CUDA_ARCH__) && defined(ANEMOI_FIELD_TABLES_%s)\n        return %s;\n#else\n        return t0 * N0INV;\n#endif\n    }\n" % (field, ("k_zero_%s - t0" % field) if n0inv32 == 0xFFFFFFFF else ("t0 * k_n0inv_%s" % field)))
+        if n0inv32 == 0xFFFFFFFF:
+            qd = "return k_zero_%s - t0;" % field
+        elif QUOTIENT_SHIFT_ADD.get(field) and (-n0inv32) % (1 << 32) == 0x30003:
+            # -p^-1 = -(3 * 0x10001) mod 2^32 (bls12_381): two shift-adds and a negation on the ALU pipe instead of an IMAD
+            qd = "{ uint32_t u = t0 + (t0 << 1); uint32_t v = u + (u << 16); return k_zero_%s - v; }" % field
+        else:
+            qd = "return t0 * k_n0inv_%s;" % field
+        cu.append("    HD static uint32_t quotient_digit(uint32_t t0) {\n#if defined(__CUDA_ARCH__) && defined(ANEMOI_FIELD_TABLES_%s)\n        %s\n#else\n        return t0 * N0INV;\n#endif\n    }\n" % (field, qd))
         # a zero that ptxas cannot see through (constant-memory load): used where a literal 0 would invite ptxas to move
         # the instruction onto the saturated FMA-heavy pipe (IMAD.X Rd, RZ, RZ, Rd / IMAD.MOV Rd, RZ) -- see fp.cuh
         cu.append("    HD static uint32_t opaque_zero() {\n#if defined(__CUDA_ARCH__) && defined(ANEMOI_FIELD_TABLES_%s)\n        return k_zero_%s;\n#else\n        return 0u;\n#endif\n    }\n" % (field, field))
