@@ -48,6 +48,17 @@ const int kFieldLimbs[ANEMOI_NUM_FIELDS] = {6, 6, 4, 4, 4, 4, 4};
 // NUM_HASH_ROUNDS: src/<field>/anemoi_2_1/mod.rs:31-32, anemoi_4_3/mod.rs:31-32
 const int kRounds[ANEMOI_NUM_FIELDS][2] = {{21, 14}, {21, 14}, {21, 14}, {19, 13}, {21, 14}, {21, 14}, {21, 14}};
 
+// the moduli (curve definitions), u64 limbs little-endian -- only the opt-in input check uses them
+const uint64_t kModulus[ANEMOI_NUM_FIELDS][6] = {
+    {0x8508c00000000001ULL, 0x170b5d4430000000ULL, 0x1ef3622fba094800ULL, 0x1a22d9f300f5138fULL, 0xc63b05c06ca1493bULL, 0x01ae3a4617c510eaULL},  // bls12_377
+    {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL, 0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL},  // bls12_381
+    {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL, 0x0000000000000000ULL, 0x0000000000000000ULL},  // bn_254
+    {0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL, 0x12ab655e9a2ca556ULL, 0x0000000000000000ULL, 0x0000000000000000ULL},  // ed_on_bls12_377
+    {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL, 0x0000000000000000ULL, 0x0000000000000000ULL},  // jubjub
+    {0x992d30ed00000001ULL, 0x224698fc094cf91bULL, 0x0000000000000000ULL, 0x4000000000000000ULL, 0x0000000000000000ULL, 0x0000000000000000ULL},  // pallas
+    {0x8c46eb2100000001ULL, 0x224698fc0994a8ddULL, 0x0000000000000000ULL, 0x4000000000000000ULL, 0x0000000000000000ULL, 0x0000000000000000ULL},  // vesta
+};
+
 int check_fi(int field, int inst) {
     if (field < 0 || field >= ANEMOI_NUM_FIELDS) return ANEMOI_B200_ERR_FIELD;
     if (inst != ANEMOI_INST_2_1 && inst != ANEMOI_INST_4_3) return ANEMOI_B200_ERR_INST;
@@ -282,6 +293,15 @@ const char* anemoi_b200_field_name(int field) {
 }
 
 // ---- device-pointer entry points ---------------------------------------------------------------
+
+int anemoi_b200_count_noncanonical_dev(int field, const uint64_t* d_elems, size_t n, uint64_t* d_count, void* stream) {
+    int rc = check_fi(field, ANEMOI_INST_2_1);
+    if (rc) return rc;
+    if (!d_count || (n && !d_elems)) return ANEMOI_B200_ERR_ARG;
+    CK(anemoi_aux_count_noncanonical(d_elems, n, kFieldLimbs[field], kModulus[field], (unsigned long long*)d_count,
+                                     (cudaStream_t)stream));
+    return ANEMOI_B200_OK;
+}
 
 int anemoi_b200_permute_dev(int field, int inst, uint64_t* d_states, size_t n, void* stream) {
     int rc = check_fi(field, inst);
@@ -680,6 +700,19 @@ int anemoi_b200_merge(int field, int inst, const uint64_t* digest_pairs, uint64_
     const size_t fb = felt_bytes(field);
     return host_call(device, digest_pairs, n * 2 * fb, out, n * fb, false, [&](void* di, void* dout, cudaStream_t st) {
         return anemoi_b200_merge_dev(field, inst, (const uint64_t*)di, (uint64_t*)dout, n, st);
+    });
+}
+
+int anemoi_b200_count_noncanonical(int field, const uint64_t* elems, size_t n, uint64_t* count, int device) {
+    int rc = check_fi(field, ANEMOI_INST_2_1);
+    if (rc) return rc;
+    if (!count || (n && !elems)) return ANEMOI_B200_ERR_ARG;
+    if (n == 0) {
+        *count = 0;
+        return ANEMOI_B200_OK;
+    }
+    return host_call(device, elems, n * felt_bytes(field), count, sizeof(uint64_t), false, [&](void* di, void* dout, cudaStream_t st) {
+        return anemoi_b200_count_noncanonical_dev(field, (const uint64_t*)di, n, (uint64_t*)dout, st);
     });
 }
 

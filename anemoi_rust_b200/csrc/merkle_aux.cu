@@ -61,7 +61,36 @@ __global__ void assemble_level_kernel(const uint64_t* __restrict__ cur, const ui
     for (int w = 0; w < n64; w++) dst[w] = src[w];
 }
 
+// one thread per element: counts the elements that are not canonical (>= p); p as n64 little-endian u64 limbs
+struct Modulus { uint64_t w[6]; };
+__global__ void count_noncanonical_kernel(const uint64_t* __restrict__ elems, unsigned long long n, int n64, Modulus p,
+                                          unsigned long long* __restrict__ count) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t* e = elems + t * n64;
+    bool lt = false, eq = true;  // lexicographic compare from the top limb
+    for (int w = n64 - 1; w >= 0; w--) {
+        const uint64_t v = e[w];
+        if (eq && v < p.w[w]) lt = true;
+        if (v != p.w[w]) eq = false;
+    }
+    if (!lt) atomicAdd(count, 1ULL);
+}
+
 }  // namespace
+
+cudaError_t anemoi_aux_count_noncanonical(const uint64_t* elems, unsigned long long n, int n64, const uint64_t* modulus,
+                                          unsigned long long* d_count, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess || n == 0) return e;
+    Modulus p;
+    for (int w = 0; w < 6; w++) p.w[w] = w < n64 ? modulus[w] : 0;
+    const int block = 256;
+    const unsigned long long blocks = (n + block - 1) / block;
+    if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
+    count_noncanonical_kernel<<<(unsigned)blocks, block, 0, stream>>>(elems, n, n64, p, d_count);
+    return cudaGetLastError();
+}
 
 cudaError_t anemoi_aux_gather_paths(const uint64_t* leaves, const uint64_t* tree, unsigned long long n_leaves, int arity,
                                     int height, int n64, const uint64_t* indices, unsigned long long n_idx,

@@ -80,6 +80,8 @@ _SIGS = {
     "anemoi_b200_comm_info": ([_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)], _i),
     "anemoi_b200_comm_destroy": ([_vp], _i),
     "anemoi_b200_pool_trim": ([_i, _sz], _i),
+    "anemoi_b200_count_noncanonical": ([_i, _vp, _sz, _vp, _i], _i),
+    "anemoi_b200_count_noncanonical_dev": ([_i, _vp, _sz, _vp, _vp], _i),
     "anemoi_b200_merkle_tree_felts": ([_i, _sz], _sz),
     "anemoi_b200_merkle_tree_dev": ([_i, _i, _i, _vp, _sz, _vp, _vp], _i),
     "anemoi_b200_merkle_open_dev": ([_i, _i, _i, _vp, _vp, _sz, _vp, _sz, _vp, _vp], _i),

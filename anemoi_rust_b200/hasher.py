@@ -317,6 +317,15 @@ class _AnemoiBase:
         return out
 
     @classmethod
+    def count_noncanonical(cls, elems):
+        """Opt-in input check: how many elements of a host limb array are >= p (the compute entries assume none)."""
+        f = cls.FIELD
+        a = _np_in(elems, f.n64)
+        out = np.zeros(1, dtype=np.uint64)
+        ffi.check(_lib.anemoi_b200_count_noncanonical(f.id, _ptr(a), a.size // f.n64, _ptr(out), cls.device))
+        return int(out[0])
+
+    @classmethod
     def merkle_root(cls, leaves, n_gpus=1):
         """Jive Merkle root of arity STATE_WIDTH over a host array of leaf digests (n, N64)."""
         f = cls.FIELD

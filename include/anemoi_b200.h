@@ -136,6 +136,11 @@ int anemoi_b200_merge(int field, int inst, const uint64_t* digest_pairs, uint64_
 int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leaves, size_t n_leaves, uint64_t* root,
                             int n_gpus);
 
+/* Opt-in input check: *count = how many of the n elements are NOT canonical (>= p). The compute entries do not check
+ * their inputs (an arkworks Fp cannot hold a non-canonical value, and the lazy-reduction bounds of the kernels assume
+ * canonical input); a host that builds limb arrays by other means can run this first. */
+int anemoi_b200_count_noncanonical(int field, const uint64_t* elems, size_t n, uint64_t* count, int device);
+
 /* AnemoiDigest::to_bytes (src/<field>/anemoi_x/digest.rs:42-46): n Montgomery elements -> n canonical
  * little-endian byte strings of 8*N64 bytes each (de-Montgomery on the device). */
 int anemoi_b200_digest_to_bytes(int field, const uint64_t* digests, uint8_t* bytes, size_t n, int device);
@@ -155,6 +160,7 @@ int anemoi_b200_hash_bytes_ragged_dev(int field, int inst, const uint8_t* d_byte
                                       size_t n_msgs, uint64_t* d_digests, void* stream);
 int anemoi_b200_merge_dev(int field, int inst, const uint64_t* d_pairs, uint64_t* d_out, size_t n, void* stream);
 int anemoi_b200_digest_to_bytes_dev(int field, const uint64_t* d_digests, uint8_t* d_bytes, size_t n, void* stream);
+int anemoi_b200_count_noncanonical_dev(int field, const uint64_t* d_elems, size_t n, uint64_t* d_count, void* stream);
 
 /* Reduce `levels` levels of a Jive Merkle tree on the device: d_leaves (n_leaves elements, not
  * modified) -> d_out (n_leaves / arity^levels elements). d_scratch must hold at least

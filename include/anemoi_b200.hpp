@@ -40,6 +40,21 @@ inline void check(int rc) {
     throw Error(rc);
 }
 
+// NCCL communicator owned by the library (anemoi_b200_comm_*): rank 0 draws the 128-byte id, the host ships it to the
+// other ranks by its own transport, every rank joins with its CUDA device current. Used by merkle_root_sharded_dev.
+struct Comm {
+    void* c = nullptr;
+    static std::array<uint8_t, 128> unique_id() {
+        std::array<uint8_t, 128> id{};
+        check(anemoi_b200_comm_unique_id(id.data()));
+        return id;
+    }
+    Comm(const std::array<uint8_t, 128>& id, int nranks, int rank) { check(anemoi_b200_comm_init_rank(id.data(), nranks, rank, &c)); }
+    Comm(const Comm&) = delete;
+    Comm& operator=(const Comm&) = delete;
+    ~Comm() { anemoi_b200_comm_destroy(c); }
+};
+
 // AnemoiDigest([Felt; 1]) -- src/<field>/anemoi_x/digest.rs:13-53
 template <int FIELD, int N64>
 struct AnemoiDigest {
@@ -99,6 +114,13 @@ struct Anemoi {
         F root{};
         check(anemoi_b200_merkle_root(FIELD, INST, STATE_WIDTH, raw(leaves.data()), leaves.size(), raw(&root), n_gpus));
         return root;
+    }
+
+    // Sharded root, one rank per GPU (device pointers on the current device, stream-ordered): per-rank sub-tree, one
+    // ncclAllGather of the partial roots issued by the library, top levels on every rank. comm == nullptr: single rank.
+    static void merkle_root_sharded_dev(const F* d_local_leaves, size_t n_local, const Comm* comm, F* d_root, void* stream) {
+        check(anemoi_b200_merkle_root_sharded_dev(FIELD, INST, STATE_WIDTH, raw(d_local_leaves), n_local, comm ? comm->c : nullptr,
+                                                  nullptr, raw(d_root), stream));
     }
 
     // Openings (authentication paths) of `indices` in the tree over `leaves`; returns the root, fills `paths`

@@ -49,6 +49,7 @@ extern "C" {
     pub fn anemoi_b200_hash_bytes_ragged(field: c_int, inst: c_int, bytes: *const u8, offsets: *const u64, n_msgs: usize, digests: *mut u64, device: c_int) -> c_int;
     pub fn anemoi_b200_merge(field: c_int, inst: c_int, digest_pairs: *const u64, out: *mut u64, n: usize, device: c_int) -> c_int;
     pub fn anemoi_b200_merkle_root(field: c_int, inst: c_int, arity: c_int, leaves: *const u64, n_leaves: usize, root: *mut u64, n_gpus: c_int) -> c_int;
+    pub fn anemoi_b200_count_noncanonical(field: c_int, elems: *const u64, n: usize, count: *mut u64, device: c_int) -> c_int;
     pub fn anemoi_b200_digest_to_bytes(field: c_int, digests: *const u64, bytes: *mut u8, n: usize, device: c_int) -> c_int;
     pub fn anemoi_b200_permute_dev(field: c_int, inst: c_int, d_states: *mut u64, n: usize, stream: *mut c_void) -> c_int;
     pub fn anemoi_b200_sbox_layer_dev(field: c_int, inst: c_int, d_states: *mut u64, n: usize, stream: *mut c_void) -> c_int;
@@ -60,6 +61,7 @@ extern "C" {
     pub fn anemoi_b200_hash_bytes_ragged_dev(field: c_int, inst: c_int, d_bytes: *const u8, d_offsets: *const u64, n_msgs: usize, d_digests: *mut u64, stream: *mut c_void) -> c_int;
     pub fn anemoi_b200_merge_dev(field: c_int, inst: c_int, d_pairs: *const u64, d_out: *mut u64, n: usize, stream: *mut c_void) -> c_int;
     pub fn anemoi_b200_digest_to_bytes_dev(field: c_int, d_digests: *const u64, d_bytes: *mut u8, n: usize, stream: *mut c_void) -> c_int;
+    pub fn anemoi_b200_count_noncanonical_dev(field: c_int, d_elems: *const u64, n: usize, d_count: *mut u64, stream: *mut c_void) -> c_int;
     pub fn anemoi_b200_merkle_reduce_dev(field: c_int, inst: c_int, arity: c_int, d_leaves: *const u64, n_leaves: usize, levels: c_int, d_scratch: *mut u64, d_out: *mut u64, stream: *mut c_void) -> c_int;
     pub fn anemoi_b200_merkle_scratch_felts(arity: c_int, n_leaves: usize) -> usize;
     pub fn anemoi_b200_merkle_root_sharded_dev(field: c_int, inst: c_int, arity: c_int, d_local_leaves: *const u64, n_local: usize, nccl_comm: *mut c_void, d_scratch: *mut u64, d_root: *mut u64, stream: *mut c_void) -> c_int;

@@ -262,3 +262,20 @@ def test_layers_in_isolation(field, inst):
         y = H.layer_batch(y, "round", r)
     y = H.layer_batch(y, "mds")
     assert np.array_equal(y, H.permutation_batch(x[: W * 5]))
+
+
+@pytest.mark.parametrize("field", ["bls12_381", "bn_254", "pallas"])
+def test_count_noncanonical(field):
+    """The opt-in input check counts exactly the elements >= p (p itself, p + 1, all-ones), none of the canonical ones."""
+    H = HASHERS[(field, "anemoi_2_1")]
+    f = H.FIELD
+    x = f.random_mont(1000, SEED + 95)
+    assert H.count_noncanonical(x) == 0
+    bad = x.copy()
+    mask = (1 << 64) - 1
+    for row, v in ((3, f.p), (500, f.p + 1), (999, (1 << (64 * f.n64)) - 1)):
+        for j in range(f.n64):
+            bad[row, j] = (v >> (64 * j)) & mask
+    bad[7] = [(((f.p - 1) >> (64 * j)) & mask) for j in range(f.n64)]   # p - 1 is canonical
+    assert H.count_noncanonical(bad) == 3
+    assert H.count_noncanonical(x[:0]) == 0
