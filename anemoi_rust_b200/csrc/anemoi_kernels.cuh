@@ -409,7 +409,7 @@ struct Tables<Variant<F, COLS, LATENCY>> : Tables<F> {};
 // Throughput form: F::BLOCK-thread blocks, F::MIN_BLOCKS resident per SM (register-capped so that the FMA-heavy pipe
 // always has 16+ warps to draw from).
 template <class F, int COLS>
-__global__ void __launch_bounds__(F::BLOCK, F::MIN_BLOCKS) anemoi_kernel(KernelArgs a) {
+__global__ void __launch_bounds__(F::BLOCK, COLS == 1 ? F::MIN_BLOCKS_2_1 : F::MIN_BLOCKS_4_3) anemoi_kernel(KernelArgs a) {
     anemoi_body<Variant<F, COLS, false>, COLS>(a);
 }
 

@@ -42,6 +42,9 @@ SPECIAL_LIMBS = {
 CARRY_CHAIN = {"bls12_377": "01", "bls12_381": "00", "bn_254": "01", "ed_on_bls12_377": "11", "jubjub": "00", "pallas": "11",
                "vesta": "11"}
 CARRY_CHAIN.update({k: v for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_CARRY_CHAIN", "").split(",") if kv)})
+MIN_BLOCKS = {"bn_254": (8, 7)}
+if os.environ.get("ANEMOI_MIN_BLOCKS_8"):
+    MIN_BLOCKS = {"__all8__": int(os.environ["ANEMOI_MIN_BLOCKS_8"])}
 # Montgomery quotient digit m = t0 * (-p^-1 mod 2^32) by shift-adds where the constant allows it (bls12_381: -0x30003)
 QUOTIENT_SHIFT_ADD = {"bls12_381": 0}
 QUOTIENT_SHIFT_ADD.update({k: int(v) for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_QUOTIENT_SHIFT_ADD", "").split(",") if kv)})
@@ -286,9 +289,16 @@ def main():
         # (<= 96 registers, no spills); N = 8: 128 x 7 = 28 warps/SM (<= 72 registers, no spills). One block fewer
         # measured 0-1.5 % slower.
         blk = 128
-        minb = int(os.environ.get("ANEMOI_MIN_BLOCKS_%d" % n32, 7 if n32 == 8 else 5))
+        # resident blocks per SM the kernels are compiled for (register cap = 65536 / (128 * blocks)): 12-limb 5 (<= 96
+        # registers), 8-limb 8 (64 registers, a few words of spills outside the hot loops; measured -1 % on the 4-3 kernels
+        # and -0.3..-0.8 % on the 2-1 kernels against 7 blocks / 72 registers, except bn_254 4-3: +0.7 %)
+        mb = MIN_BLOCKS.get(field, (8, 8) if n32 == 8 else (5, 5))
+        if "__all8__" in MIN_BLOCKS and n32 == 8:
+            mb = (MIN_BLOCKS["__all8__"],) * 2
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
-        cu.append("    static constexpr int MIN_BLOCKS = %d;\n" % minb)
+        cu.append("    static constexpr int MIN_BLOCKS_2_1 = %d;\n" % mb[0])
+        cu.append("    static constexpr int MIN_BLOCKS_4_3 = %d;\n" % mb[1])
+        cu.append("    static constexpr int MIN_BLOCKS = MIN_BLOCKS_2_1;\n")
         cc = CARRY_CHAIN.get(field, "00")
         cu.append("    // fp.cuh: carry fix-ups chained through the carry flag, per kernel instantiation (CARRY_CHAIN itself is what a\n    // bare F gets: the diagnostic layer kernel and the host emulation)\n")
         cu.append("    static constexpr bool CARRY_CHAIN_2_1 = %s;\n" % ("true" if cc[0] == "1" else "false"))
