@@ -218,6 +218,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly ONE JSON line: native libraries (NCCL's version banner, for one) write to file descriptor 1
+    # behind Python's back, so fd 1 is pointed at stderr for the duration of the run and the line goes to the saved fd
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -495,9 +501,12 @@ def main():
         else:
             line["merkle_check"] = check
         barrier()
+        # While rank 0 drives all N GPUs from its own process, the other ranks must leave their GPUs idle: they wait on a
+        # key of the rendezvous store (a CPU-side wait), not in an NCCL barrier whose kernel would spin on their device.
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
             # the single-process C-ABI forms a Rust host would call: one host thread + stream per device inside the call,
-            # NCCL all-gather between them (ncclCommInitAll); the other ranks idle at the barrier below meanwhile
+            # NCCL all-gather between them (ncclCommInitAll)
             try:
                 Hc.device = 0
                 r_multi = Hc.merkle_root(leaves_c, n_gpus=world)
@@ -510,6 +519,9 @@ def main():
             except Exception as exc:  # report, do not lose the line
                 line["c_abi_multi_matches"] = False
                 line["c_abi_multi"] = {"error": str(exc)[:300]}
+            store.set("anemoi_c_abi_multi_done", "1")
+        else:
+            store.wait(["anemoi_c_abi_multi_done"])
         barrier()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
@@ -521,7 +533,8 @@ def main():
                                 "sample": "2^%d pairs of the same workload (seed 0x%X), OpenMP over all host threads" % (args.cpu_sample_log2, SEED),
                                 "gpu_matches_cpu_on_sample": bool(np.array_equal(gpu_out, cpu_out))}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
