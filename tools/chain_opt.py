@@ -13,7 +13,8 @@ Method: dictionary-based sliding window with a SEARCHED dictionary.
     (helpers such as 2, 4, 6 allowed, freed as soon as they are dead);
   * the exponent is parsed left to right into windows whose values are in D by dynamic programming (minimum number of
     multiplies; window length <= MAXLEN bits);
-  * D is optimised by simulated annealing on   cost = SQR_COST * squarings + MUL_COST * multiplies;
+  * D is optimised by simulated annealing on   cost = SQR_COST * squarings + MUL_COST * multiplies  (moves draw new
+    entries from the windows that actually occur in the exponent, weighted by how often they do);
   * the result is compiled to the interpreter's ISA (SQR n / MUL slot / LD slot / ST slot) with a linear-scan slot
     allocator and VERIFIED by executing it on exponents (tools/gen_params.py: check_program).
 
@@ -132,7 +133,16 @@ def cost_of(bits, D, maxlen, cs, cm):
 
 def anneal(bits, K, maxlen, cs, cm, iters, seed):
     rnd = random.Random(seed)
-    cands = list(range(3, 1 << maxlen, 2))
+    # candidate dictionary entries: only odd values that OCCUR as a window of the exponent can ever be used by the parse;
+    # listing each as often as it occurs biases the moves towards the frequent ones (periodic exponents have few)
+    cands = []
+    for i in range(len(bits)):
+        if bits[i] == "1":
+            v = 0
+            for l in range(1, min(maxlen, len(bits) - i) + 1):
+                v = (v << 1) | (bits[i + l - 1] == "1")
+                if (v & 1) and v > 1:
+                    cands.append(v)
     D = set(range(1, 2 * min(K, 16), 2))
     cur = cost_of(bits, D, maxlen, cs, cm)
     best, bestD = cur, set(D)
@@ -246,6 +256,7 @@ def main():
     ap.add_argument("--maxlen", type=int, default=9)
     ap.add_argument("--iters", type=int, default=30000)
     ap.add_argument("--seeds", type=int, default=4)
+    ap.add_argument("--seed-base", type=int, default=1000)
     ap.add_argument("--out", default=os.path.join(ROOT, "tools", "chains.json"))
     args = ap.parse_args()
     params = json.load(open(os.path.join(ROOT, "tests", "golden", "params.json")))
@@ -260,7 +271,7 @@ def main():
         ref_cost = cs * ref_s + cm * ref_m
         best = None
         for seed in range(args.seeds):
-            c, D = anneal(bits, args.slots, args.maxlen, cs, cm, args.iters, 1000 + seed)
+            c, D = anneal(bits, args.slots, args.maxlen, cs, cm, args.iters, args.seed_base + seed)
             prog, nslots = compile_program(bits, D, args.maxlen)
             s, m = run_program(prog, nslots, e)
             cost = cs * s + cm * m

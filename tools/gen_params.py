@@ -64,7 +64,7 @@ SPECIAL_LIMBS.update({k: [int(x) for x in v.split(":") if x != ""] for k, v in
 # dictionary, stored in tools/chains.json and re-verified here): fewer multiplies than the reference's chain AND 10-13
 # live values instead of 19-28, which keeps the slot file L2-resident (no local-memory write-back to HBM).
 CHAIN_SOURCE = {"bls12_377": "searched", "bls12_381": "searched", "bn_254": "searched", "ed_on_bls12_377": "searched",
-                "jubjub": "searched", "pallas": "searched", "vesta": "reference"}
+                "jubjub": "searched", "pallas": "searched", "vesta": "searched"}
 CHAIN_SOURCE.update({k: v for k, v in (kv.split("=") for kv in os.environ.get("ANEMOI_CHAIN_SOURCE", "").split(",") if kv)})
 CHAINS_JSON = os.environ.get("ANEMOI_CHAINS_JSON", os.path.join(ROOT, "tools", "chains.json"))
 
