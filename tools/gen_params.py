@@ -295,6 +295,8 @@ def main():
         mb = MIN_BLOCKS.get(field, (8, 8) if n32 == 8 else (5, 5))
         if "__all8__" in MIN_BLOCKS and n32 == 8:
             mb = (MIN_BLOCKS["__all8__"],) * 2
+        if os.environ.get("ANEMOI_MIN_BLOCKS_12") and n32 == 12:
+            mb = (int(os.environ["ANEMOI_MIN_BLOCKS_12"]),) * 2
         cu.append("    static constexpr int BLOCK = %d;\n" % blk)
         cu.append("    static constexpr int MIN_BLOCKS_2_1 = %d;\n" % mb[0])
         cu.append("    static constexpr int MIN_BLOCKS_4_3 = %d;\n" % mb[1])
