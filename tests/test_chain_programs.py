@@ -109,3 +109,25 @@ def test_chains_json_matches_generated_header():
             continue
         assert [tuple(x) for x in rec["program"]] == program(field)
         assert rec["slots"] == const(field, "SLOTS")
+
+
+def test_chain_search_tool_produces_valid_programs():
+    """tools/chain_opt.py end to end on a short budget: whatever dictionary the annealer lands on, the compiled program
+    must compute x^INV_ALPHA within its slot file (the tool asserts that itself; here it is exercised in the suite)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import chain_opt
+
+    for field in ("pallas", "bn_254", "bls12_381"):
+        fp = PARAMS[field]
+        e = int(fp["inv_alpha"])
+        bits = bin(e)[2:]
+        cs, cm = chain_opt.mac_costs(2 * fp["n64"])
+        (cost, nsq, nmul), D = chain_opt.anneal(bits, 10, 10, cs, cm, 300, 7)
+        prog, slots = chain_opt.compile_program(bits, D, 10)
+        s, m = chain_opt.run_program(prog, slots, e)
+        assert (s, m) == (nsq, nmul) and cost == cs * s + cm * m
+        assert slots <= 12 and 1 in D
+        got, _, _ = run_accumulator_machine(prog, slots, 1, lambda a, b: a + b, lambda a: 2 * a)
+        assert got == e
