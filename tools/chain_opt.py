@@ -52,6 +52,33 @@ def parse(bits, D, maxlen):
             v = (v << 1) | (bits[i + l - 1] == "1")
             if (v & 1) and v in D and dp[i + l] + 1 < dp[i]:
                 dp[i], ch[i] = dp[i + l] + 1, (l, v)
+    # self-doubling: at position i the accumulator holds x^A with A = the first i bits; if the NEXT s bits spell A again
+    # (leading zeros allowed), then ST t; SQR s; MUL t covers them with one multiply. Periodic exponents (Pallas / Vesta
+    # start with 126 bits of 0011...) double their prefix this way: 14 -> 30 -> 62 -> 126 bits in three multiplies.
+    # (A second backward pass: the transition at i needs dp[i + s], which the first pass has already settled.)
+    e_val = int(bits, 2)
+    for i in range(n - 1, 1, -1):
+        A = e_val >> (n - i)
+        b = A.bit_length()
+        for sdbl in range(b, min(n - i, b + 8) + 1):
+            if int(bits[i:i + sdbl], 2) == A and dp[i + sdbl] + 1 < dp[i]:
+                dp[i], ch[i] = dp[i + sdbl] + 1, (sdbl, -1)
+        # a better dp[i] can improve the zero-bit predecessors that simply step onto it
+        j = i - 1
+        while j >= 0 and bits[j] == "0" and dp[j + 1] < dp[j]:
+            dp[j], ch[j] = dp[j + 1], (1, 0)
+            j -= 1
+    # windows that END where a self-double starts may now be cheaper: one more forward-independent relaxation pass
+    for i in range(n - 1, -1, -1):
+        if bits[i] == "0":
+            if dp[i + 1] < dp[i]:
+                dp[i], ch[i] = dp[i + 1], (1, 0)
+            continue
+        v = 0
+        for l in range(1, min(maxlen, n - i) + 1):
+            v = (v << 1) | (bits[i + l - 1] == "1")
+            if (v & 1) and v in D and dp[i + l] + 1 < dp[i]:
+                dp[i], ch[i] = dp[i + l] + 1, (l, v)
     best = None
     v = 0
     for l in range(1, min(maxlen, n) + 1):
@@ -67,6 +94,12 @@ def parse(bits, D, maxlen):
         if v == 0:
             pending += 1
             i += 1
+        elif v == -1:  # self-double: the squarings still pending belong to the value that gets stored
+            if pending:
+                ops.append((pending, 0))
+            ops.append((l, -1))
+            pending = 0
+            i += l
         else:
             ops.append((pending + l, v))
             pending = 0
@@ -182,7 +215,7 @@ def compile_program(bits, D, maxlen):
     run_uses = {}
     for j, item in enumerate(run):
         v = item if j == 0 else item[1]
-        if v:
+        if v and v > 0:
             run_uses[v] = len(steps) + j
     for v, t in run_uses.items():
         last_use[v] = max(last_use.get(v, -1), t)
@@ -217,7 +250,18 @@ def compile_program(bits, D, maxlen):
     first = run[0]
     if acc != first:
         prog.append((OP_LD, slot_of[first]))
+    dbl_slot = None
     for j, (nsq, v) in enumerate(run[1:], start=1):
+        if v == -1:  # self-double: the accumulator times its own 2^nsq-th power
+            if dbl_slot is None:  # one scratch slot serves every self-double (each value is dead after its multiply)
+                release(len(steps) + j - 1)
+                if free:
+                    dbl_slot = free.pop()
+                else:
+                    dbl_slot = nslots
+                    nslots += 1
+            prog += [(OP_ST, dbl_slot), (OP_SQR, nsq), (OP_MUL, dbl_slot)]
+            continue
         prog.append((OP_SQR, nsq))
         if v:
             prog.append((OP_MUL, slot_of[v]))
