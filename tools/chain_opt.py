@@ -12,7 +12,8 @@ Method: dictionary-based sliding window with a SEARCHED dictionary.
   * dictionary D = a set of <= K odd exponents (1 in D); it is built once per S-box by a short addition sequence
     (helpers such as 2, 4, 6 allowed, freed as soon as they are dead);
   * the exponent is parsed left to right into windows whose values are in D by dynamic programming (minimum number of
-    multiplies; window length <= MAXLEN bits);
+    multiplies; window length <= MAXLEN bits); the parse also knows PREFIX SELF-DOUBLING -- where the next s bits spell
+    the whole prefix again, ST t; SQR s; MUL t covers them with one multiply (periodic exponents: Pallas, Vesta);
   * D is optimised by simulated annealing on   cost = SQR_COST * squarings + MUL_COST * multiplies  (moves draw new
     entries from the windows that actually occur in the exponent, weighted by how often they do);
   * the result is compiled to the interpreter's ISA (SQR n / MUL slot / LD slot / ST slot) with a linear-scan slot
@@ -33,6 +34,24 @@ OP_SQR, OP_MUL, OP_LD, OP_ST = 0, 1, 2, 3
 
 def mac_costs(n32):
     return n32 * (n32 + 1) // 2 + n32 * n32 + n32, 2 * n32 * n32 + n32  # squaring, multiply
+
+
+_SELF_DOUBLES = {}
+
+
+def self_doubles(bits):
+    """{position i: [s, ...]} such that the s bits after position i spell the first i bits again (a property of the
+    exponent alone, computed once)."""
+    if bits not in _SELF_DOUBLES:
+        n, e_val, table = len(bits), int(bits, 2), {}
+        for i in range(2, n):
+            A = e_val >> (n - i)
+            b = A.bit_length()
+            for s in range(b, min(n - i, b + 8) + 1):
+                if int(bits[i:i + s], 2) == A:
+                    table.setdefault(i, []).append(s)
+        _SELF_DOUBLES[bits] = table
+    return _SELF_DOUBLES[bits]
 
 
 def parse(bits, D, maxlen):
@@ -56,12 +75,9 @@ def parse(bits, D, maxlen):
     # (leading zeros allowed), then ST t; SQR s; MUL t covers them with one multiply. Periodic exponents (Pallas / Vesta
     # start with 126 bits of 0011...) double their prefix this way: 14 -> 30 -> 62 -> 126 bits in three multiplies.
     # (A second backward pass: the transition at i needs dp[i + s], which the first pass has already settled.)
-    e_val = int(bits, 2)
     for i in range(n - 1, 1, -1):
-        A = e_val >> (n - i)
-        b = A.bit_length()
-        for sdbl in range(b, min(n - i, b + 8) + 1):
-            if int(bits[i:i + sdbl], 2) == A and dp[i + sdbl] + 1 < dp[i]:
+        for sdbl in self_doubles(bits).get(i, ()):
+            if dp[i + sdbl] + 1 < dp[i]:
                 dp[i], ch[i] = dp[i + sdbl] + 1, (sdbl, -1)
         # a better dp[i] can improve the zero-bit predecessors that simply step onto it
         j = i - 1
