@@ -72,3 +72,36 @@ def test_argument_errors_without_a_device():
 
         with pytest.raises(A.NoDeviceError):
             A.AnemoiBls12_381_2_1.compress([0, 1])
+
+
+def test_sharded_plan_in_c_matches_python_plan():
+    """The partition plan lives twice: merkle.plan (host logic, gloo-tested) and shard_plan in api.cu (what the C-ABI call
+    uses). anemoi_b200_merkle_sharded_scratch_felts exposes the C side's view: local scratch + partial roots + gathered
+    roots + top-level scratch, 0 when the ranks do not split the tree into whole sub-trees."""
+    from anemoi_rust_b200 import ffi, merkle
+
+    lib = ffi.lib
+    for arity, total, world in ((4, 4 ** 13, 1), (4, 4 ** 13, 2), (4, 4 ** 13, 4), (4, 4 ** 13, 8), (2, 2 ** 24, 8), (2, 2 ** 10, 2),
+                                (4, 4 ** 5, 2), (4, 4 ** 3, 1)):
+        n_local = total // world
+        _, _, roots, _ = merkle.plan(total, arity, world)
+        gathered = roots * world
+        exp = (lib.anemoi_b200_merkle_scratch_felts(arity, n_local) + roots + gathered +
+               lib.anemoi_b200_merkle_scratch_felts(arity, gathered))
+        assert lib.anemoi_b200_merkle_sharded_scratch_felts(arity, n_local, world) == exp
+    assert lib.anemoi_b200_merkle_sharded_scratch_felts(4, 3 * 4 ** 3, 1) == 0      # 192 leaves: not a power of 4
+    assert lib.anemoi_b200_merkle_sharded_scratch_felts(4, 4 ** 3, 3) == 0          # 3 ranks x 64 leaves
+    assert lib.anemoi_b200_merkle_sharded_scratch_felts(4, 0, 2) == 0
+    # argument errors of the sharded entry are reported before any CUDA / NCCL call
+    import ctypes
+
+    import numpy as np
+
+    z = np.zeros(8, dtype=np.uint64)
+    p = ctypes.c_void_p(z.ctypes.data)
+    assert lib.anemoi_b200_merkle_root_sharded_dev(5, 1, 2, p, 16, None, None, p, None) == ffi.ERR_ARITY
+    assert lib.anemoi_b200_merkle_root_sharded_dev(5, 1, 4, p, 0, None, None, p, None) == ffi.ERR_LENGTH
+    assert lib.anemoi_b200_merkle_root_sharded_dev(5, 1, 4, None, 16, None, None, p, None) == ffi.ERR_ARG
+    assert lib.anemoi_b200_merkle_root_sharded_dev(5, 1, 4, p, 48, None, None, p, None) == ffi.ERR_LENGTH
+    assert lib.anemoi_b200_count_noncanonical(9, p, 1, p, 0) == ffi.ERR_FIELD
+    assert lib.anemoi_b200_comm_init_rank(None, 2, 0, None) == ffi.ERR_ARG
