@@ -8,9 +8,9 @@
 //
 // Mapping: Anemoi-2-1 (1 column) -> 1 thread per state; Anemoi-4-3 (2 columns) -> 2 adjacent lanes per
 // state, which exchange their columns with warp shuffles for the linear layer (the two S-boxes of a
-// round, > 99 % of the work, are independent). x^(1/alpha) runs a per-field ladder (sliding window or the
-// reference's own addition chain -- any chain gives the same canonical residue) whose table lives in
-// per-thread local memory.
+// round, > 99 % of the work, are independent). x^(1/alpha) runs a per-field addition chain on a small accumulator
+// machine (any chain gives the same canonical residue as the reference's; these are searched for few multiplies and
+// few live values, tools/chain_opt.py) whose slots live in per-thread local memory.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -55,13 +55,14 @@ FPQ void store_felt(uint32_t* p, const uint32_t (&r)[N], int vec16) {
 
 // x^INV_ALPHA -- replaces sbox::exp_by_inv_alpha (src/<field>/sbox.rs). Any addition chain yields the same
 // canonical residue as the reference's hard-coded one, so each field runs whichever ladder measured fastest
-// (tools/gen_params.py). The ladder's table / slots are a dynamically indexed per-thread array, i.e. LOCAL
+// (tools/gen_params.py: CHAIN_SOURCE). The ladder's slots are a dynamically indexed per-thread array, i.e. LOCAL
 // memory (L1/L2-backed): one 32/48-byte entry is touched per ~5 squarings (~5 k cycles per thread), so its
-// latency is irrelevant, while shared memory would cap the resident warps (8 entries x 48 B x 512 threads =
-// 192 KB per SM) and forbid the larger tables. Measured: +2-5 % on every field against the shared-memory table.
+// latency is irrelevant, while shared memory would cap the resident warps (measured: 2-5 % slower on every field).
+// What matters is how MANY slots there are: the slot file of all resident threads should stay L2- (ideally L1-)
+// resident, or its write-back reaches HBM.
 //
-// (1) Sliding-window ladder: T[k] = x^(2k+1); the schedule {squarings, entry} comes from constant memory
-//     (warp-uniform, no divergence). x^2 and the running odd power stay in registers while T is built.
+// (1) Sliding-window ladder (round 1; still selectable): T[k] = x^(2k+1); the schedule {squarings, entry} comes from
+//     constant memory (warp-uniform, no divergence). x^2 and the running odd power stay in registers while T is built.
 template <class F>
 FPQ void pow_window(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
     constexpr int N = F::N;
@@ -100,10 +101,11 @@ FPQ void pow_window(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
     }
 }
 
-// (2) Accumulator machine running the reference crate's own addition chain, compiled onto slots by a linear-scan
-//     allocator in tools/gen_params.py: SQR n, MUL slot, LD slot, ST slot; slot 0 = x. Used where it measured
-//     faster than the window ladder: bls12_381 (378 S + 76 M in 28 slots vs 379 S + 81 M), Pallas (252 S + 43 M in
-//     11 slots vs 250 S + 56 M), Vesta (248 S + 45 M in 12 slots).
+// (2) Accumulator machine: SQR n, MUL slot, LD slot, ST slot; slot 0 = x; the program is warp-uniform and comes from
+//     constant memory. It runs the chains of tools/chains.json (searched by tools/chain_opt.py: 6-14 slots, 1-4 % less
+//     MAC32 work than the reference's chains), or the reference crate's own chain compiled onto slots by a linear-scan
+//     allocator (tools/gen_params.py; round 1: 11-28 slots). tests/test_chain_programs.py executes the generated
+//     programs on the CPU.
 template <class F>
 FPQ void pow_program(uint32_t (&acc)[F::N], const uint32_t (&x)[F::N]) {
     constexpr int N = F::N;

@@ -763,7 +763,6 @@ int shard_plan(int arity, size_t n_local, int world, ShardPlan* plan) {
     return ANEMOI_B200_OK;
 }
 
-thread_local char g_nccl_err[160] = "";
 int nccl_fail(int code, const char* what) {
     const anemoi::nccl::Api& nc = anemoi::nccl::api();
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, nc.ok ? nc.GetErrorString(code) : "libnccl.so.2 could not be loaded");
