@@ -279,3 +279,25 @@ def test_count_noncanonical(field):
     bad[7] = [(((f.p - 1) >> (64 * j)) & mask) for j in range(f.n64)]   # p - 1 is canonical
     assert H.count_noncanonical(bad) == 3
     assert H.count_noncanonical(x[:0]) == 0
+
+
+@pytest.mark.parametrize("field,inst", [("pallas", "anemoi_4_3"), ("ed_on_bls12_377", "anemoi_2_1"), ("bn_254", "anemoi_4_3"),
+                                        ("bls12_377", "anemoi_4_3"), ("bls12_381", "anemoi_2_1")])
+def test_latency_and_throughput_forms_agree(field, inst):
+    """The same states through every launch geometry: the latency form (one warp per block, unchained carries; <= 2 warps
+    per SM sub-partition), the throughput kernel with 32-thread blocks, and with 128-thread blocks -- identical limbs, and
+    equal to the oracle on the common prefix. (For kernels whose throughput form is unchained the two forms are one kernel.)"""
+    H = HASHERS[(field, inst)]
+    fi, ii = ids(field, inst)
+    f, W = H.FIELD, H.STATE_WIDTH
+    cols = W // 2
+    sizes = [100, 17000 // cols, 19500 // cols, 45000 // cols]   # lat, lat (many blocks), 32-thread throughput, 128-thread
+    x = f.random_mont(sizes[-1] * W, SEED + 97)
+    ref = C.compress(fi, ii, W, x[: 100 * W])
+    outs = [H.compress_k_batch(x[: n * W], W) for n in sizes]
+    for n, o in zip(sizes, outs):
+        assert np.array_equal(o[:100], ref), "n = %d" % n
+    for n, o in zip(sizes[:-1], outs[:-1]):
+        assert np.array_equal(o, outs[-1][:n]), "n = %d differs from the largest batch" % n
+    ffi.check(ffi.lib.anemoi_b200_pool_trim(0, 0))   # hand the cached device buffers back; the next call re-allocates
+    assert np.array_equal(H.compress_k_batch(x[: 100 * W], W), ref)
