@@ -777,6 +777,7 @@ int nccl_fail(int code, const char* what) {
 // Single-process communicators over devices 0..n-1 (ncclCommInitAll), created once per n and kept for the life of
 // the process (communicator setup costs ~100 ms; the all-gather itself is microseconds).
 std::mutex g_comm_mu;
+std::mutex g_multi_gpu_turn;
 std::vector<anemoi::nccl::comm_t> g_all_comms[kMaxDevices + 1];
 
 int single_process_comms(int n_gpus, std::vector<anemoi::nccl::comm_t>* out) {
@@ -916,7 +917,10 @@ int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leav
     rc = shard_plan(arity, slice, n_gpus, &plan);
     if (rc) return rc;
     std::vector<anemoi::nccl::comm_t> comms(n_gpus, nullptr);
+    // the cached single-process communicators serve one collective at a time: concurrent multi-GPU calls take turns
+    std::unique_lock<std::mutex> turn(g_multi_gpu_turn, std::defer_lock);
     if (n_gpus > 1) {
+        turn.lock();
         rc = single_process_comms(n_gpus, &comms);
         if (rc) return rc;
     }
