@@ -928,12 +928,17 @@ int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leav
     // every device got through phase 1, so that no rank is missing from the collective): sub-tree, all-gather, top levels
     // -- redundantly on every device, as in the multi-process form; device 0 returns the root.
     struct PerDevice {
-        cudaStream_t st = nullptr;
-        DevBuf leaves, root;
+        cudaStream_t st = nullptr, copy = nullptr;
+        DevBuf leaves, level1, root;
         int rc = ANEMOI_B200_OK;
         std::string err;
     };
     std::vector<PerDevice> dev(n_gpus);
+    // Big slices are uploaded in chunks on a second stream while the FIRST tree level of the chunks already there is
+    // being hashed (a level-1 node needs only its own `arity` leaves): the 2 GiB upload of a 2^26-leaf tree hides behind
+    // compute instead of preceding it. The remaining levels then start from the level-1 array.
+    const size_t level1_nodes = plan.local_levels >= 1 ? slice / (size_t)arity : 0;
+    const int chunks = (level1_nodes >= ((size_t)1 << 20) && level1_nodes % 8 == 0) ? 8 : 0;
     auto run_phase = [&](int phase) {
         auto body = [&](int g) {
             PerDevice& d = dev[g];
@@ -944,11 +949,39 @@ int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leav
                     CK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
                     cudaError_t e = d.leaves.alloc_async(slice * fb, d.st);
                     if (e == cudaSuccess) e = d.root.alloc_async(fb, d.st);
+                    if (e == cudaSuccess && chunks) e = d.level1.alloc_async(level1_nodes * fb, d.st);
                     if (e != cudaSuccess) return cuda_fail(e, "device allocation");
-                    CK(cudaMemcpyAsync(d.leaves.p, leaves + (size_t)g * slice * words, slice * fb, cudaMemcpyHostToDevice, d.st));
+                    const uint64_t* src = leaves + (size_t)g * slice * words;
+                    if (!chunks) {
+                        CK(cudaMemcpyAsync(d.leaves.p, src, slice * fb, cudaMemcpyHostToDevice, d.st));
+                        return ANEMOI_B200_OK;
+                    }
+                    CK(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+                    cudaEvent_t ready;
+                    CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+                    CK(cudaEventRecord(ready, d.st));           // the buffers exist (stream-ordered allocation) ...
+                    CK(cudaStreamWaitEvent(d.copy, ready, 0));  // ... before the copy stream writes into them
+                    CK(cudaEventDestroy(ready));
+                    const size_t nodes_per_chunk = level1_nodes / (size_t)chunks, leaves_per_chunk = nodes_per_chunk * (size_t)arity;
+                    const int mode = arity == 2 ? anemoi::MODE_COMPRESS : anemoi::MODE_COMPRESS4;
+                    for (int c = 0; c < chunks; c++) {
+                        uint64_t* d_chunk = (uint64_t*)d.leaves.p + (size_t)c * leaves_per_chunk * words;
+                        CK(cudaMemcpyAsync(d_chunk, src + (size_t)c * leaves_per_chunk * words, leaves_per_chunk * fb,
+                                           cudaMemcpyHostToDevice, d.copy));
+                        cudaEvent_t arrived;
+                        CK(cudaEventCreateWithFlags(&arrived, cudaEventDisableTiming));
+                        CK(cudaEventRecord(arrived, d.copy));
+                        CK(cudaStreamWaitEvent(d.st, arrived, 0));
+                        CK(cudaEventDestroy(arrived));
+                        int r1 = launch(field, inst, mode, d_chunk, (uint64_t*)d.level1.p + (size_t)c * nodes_per_chunk * words, nullptr,
+                                        nodes_per_chunk, 0, d.st);
+                        if (r1) return r1;
+                    }
                     return ANEMOI_B200_OK;
                 }
-                int r = anemoi_b200_merkle_root_sharded_dev(field, inst, arity, (const uint64_t*)d.leaves.p, slice, comms[g], nullptr,
+                // the sharded entry continues from the level-1 array when phase 1 already hashed the leaves
+                const uint64_t* d_from = chunks ? (const uint64_t*)d.level1.p : (const uint64_t*)d.leaves.p;
+                int r = anemoi_b200_merkle_root_sharded_dev(field, inst, arity, d_from, chunks ? level1_nodes : slice, comms[g], nullptr,
                                                             (uint64_t*)d.root.p, d.st);
                 cudaError_t e = cudaSuccess;
                 if (!r && g == 0 && (e = cudaMemcpyAsync(root, d.root.p, fb, cudaMemcpyDeviceToHost, d.st)) != cudaSuccess)
@@ -980,8 +1013,13 @@ int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leav
         if (!d.st) continue;
         DeviceScope scope(g);
         d.leaves.release();
+        d.level1.release();
         d.root.release();
         cudaStreamSynchronize(d.st);
+        if (d.copy) {
+            cudaStreamSynchronize(d.copy);
+            cudaStreamDestroy(d.copy);
+        }
         cudaStreamDestroy(d.st);
     }
     return rc;

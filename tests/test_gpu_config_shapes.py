@@ -102,3 +102,25 @@ def test_deeper_trees_vs_oracle(field, inst, height):
     assert np.array_equal(root, exp_root)
     roots = H.merkle_verify(leaves[idx.astype(np.int64)], idx, paths)
     assert np.array_equal(roots, np.repeat(exp_root, len(idx), axis=0))
+
+
+@pytest.mark.parametrize("field,inst,height", [("pallas", "anemoi_4_3", 11), ("bls12_381", "anemoi_2_1", 21)])
+def test_host_pointer_root_with_chunked_upload(field, inst, height):
+    """Trees big enough (>= 2^20 level-1 nodes) that anemoi_b200_merkle_root uploads the leaves in chunks and hashes the
+    first level of each chunk while the next one is still in flight: the root must equal the device-resident build of the
+    same leaves (itself checked against the oracle on the smaller trees above), and a sub-tree root the oracle can afford."""
+    import torch
+
+    from anemoi_rust_b200 import merkle
+
+    H = HASHERS[(field, inst)]
+    fi, ii = ids(field, inst)
+    f, ar = H.FIELD, H.STATE_WIDTH
+    n = ar ** height
+    leaves = f.random_mont(n, SEED + 5)
+    got = H.merkle_root(leaves)
+    dev = merkle.merkle_root_device(H, torch.from_numpy(leaves.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(got, dev.cpu().numpy().view(np.uint64))
+    sub = ar ** (6 if ar == 4 else 11)
+    assert np.array_equal(H.merkle_root(leaves[:sub]), C.merkle_root(fi, ii, ar, leaves[:sub]))
