@@ -219,6 +219,67 @@ int host_call(int device, const void* in, size_t in_bytes, void* out, size_t out
     return rc;
 }
 
+// Host wrapper for big batches of INDEPENDENT units (Jive compress): the batch goes up, through the kernel and back in
+// `chunks` pieces on separate streams -- upload of piece c+1 and download of piece c-1 overlap the hashing of piece c,
+// and the pieces alternate between two compute streams so that the next one starts filling SMs while the previous one
+// drains (one stream would pay a partial last wave per piece). body(d_in, d_out, n_units, stream) enqueues one piece.
+template <class Body>
+int host_call_chunked(int device, const void* in, size_t in_unit, void* out, size_t out_unit, size_t n, int chunks, Body body) {
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    cudaStream_t s_main = nullptr, s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
+    int rc = ANEMOI_B200_OK;
+    auto fail = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == ANEMOI_B200_OK) rc = cuda_fail(e, what);
+        return e != cudaSuccess;
+    };
+    fail(cudaStreamCreateWithFlags(&s_main, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!rc) fail(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!rc) fail(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; i < 2 && !rc; i++) fail(cudaStreamCreateWithFlags(&s_cmp[i], cudaStreamNonBlocking), "cudaStreamCreate");
+    {
+        DevBuf d_in, d_out;  // allocated and freed on s_main, which is idle in between
+        if (!rc) fail(d_in.alloc_async(n * in_unit, s_main), "device allocation");
+        if (!rc) fail(d_out.alloc_async(n * out_unit, s_main), "device allocation");
+        if (!rc) fail(cudaStreamSynchronize(s_main), "device allocation");  // the buffers exist before the other streams use them
+        const uint8_t* h_in = static_cast<const uint8_t*>(in);
+        uint8_t* h_out = static_cast<uint8_t*>(out);
+        for (int c = 0; c < chunks && !rc; c++) {
+            const size_t lo = n * (size_t)c / (size_t)chunks, hi = n * (size_t)(c + 1) / (size_t)chunks;
+            if (hi == lo) continue;
+            uint8_t* di = static_cast<uint8_t*>(d_in.p) + lo * in_unit;
+            uint8_t* dout = static_cast<uint8_t*>(d_out.p) + lo * out_unit;
+            cudaStream_t sc = s_cmp[c & 1];
+            cudaEvent_t up = nullptr, done = nullptr;
+            if (fail(cudaMemcpyAsync(di, h_in + lo * in_unit, (hi - lo) * in_unit, cudaMemcpyHostToDevice, s_in), "H2D copy")) break;
+            if (fail(cudaEventCreateWithFlags(&up, cudaEventDisableTiming), "cudaEventCreate")) break;
+            fail(cudaEventRecord(up, s_in), "cudaEventRecord");
+            fail(cudaStreamWaitEvent(sc, up, 0), "cudaStreamWaitEvent");
+            cudaEventDestroy(up);
+            if (rc) break;
+            rc = body(di, dout, hi - lo, sc);
+            if (rc) break;
+            if (fail(cudaEventCreateWithFlags(&done, cudaEventDisableTiming), "cudaEventCreate")) break;
+            fail(cudaEventRecord(done, sc), "cudaEventRecord");
+            fail(cudaStreamWaitEvent(s_out, done, 0), "cudaStreamWaitEvent");
+            cudaEventDestroy(done);
+            if (rc) break;
+            fail(cudaMemcpyAsync(h_out + lo * out_unit, dout, (hi - lo) * out_unit, cudaMemcpyDeviceToHost, s_out), "D2H copy");
+        }
+        // everything must have finished before the buffers are released (and before the caller reads `out`)
+        cudaStream_t all[4] = {s_in, s_cmp[0], s_cmp[1], s_out};
+        for (cudaStream_t st : all)
+            if (st) fail(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    }
+    cudaStream_t all[5] = {s_main, s_in, s_cmp[0], s_cmp[1], s_out};
+    for (cudaStream_t st : all)
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    return rc;
+}
+
 int merkle_check(int field, int inst, int arity) {
     int rc = check_fi(field, inst);
     if (rc) return rc;
@@ -575,6 +636,11 @@ int anemoi_b200_compress(int field, int inst, int k, const uint64_t* in, uint64_
     if (n == 0) return ANEMOI_B200_OK;
     if (!in || !out) return ANEMOI_B200_ERR_ARG;
     const size_t fb = felt_bytes(field);
+    if (n >= ((size_t)1 << 19))  // big batch: pipeline upload / hashing / download in 4 pieces
+        return host_call_chunked(device, in, width_of(inst) * fb, out, per * fb, n, 4,
+                                 [&](void* di, void* dout, size_t m, cudaStream_t st) {
+                                     return anemoi_b200_compress_dev(field, inst, k, (const uint64_t*)di, (uint64_t*)dout, m, st);
+                                 });
     return host_call(device, in, n * width_of(inst) * fb, out, n * per * fb, false, [&](void* di, void* dout, cudaStream_t st) {
         return anemoi_b200_compress_dev(field, inst, k, (const uint64_t*)di, (uint64_t*)dout, n, st);
     });
