@@ -432,11 +432,14 @@ def main():
             torch.cuda.synchronize()
             hl = host_leaves.numpy().view(np.uint64)
             H4.device = local_rank
-            H4.merkle_root(hl[: 4 ** 6])     # warm the library pool / stream path
-            t0 = time.perf_counter()
-            r_host = H4.merkle_root(hl)
-            e2e_ms = (time.perf_counter() - t0) * 1e3
-            line["merkle"]["e2e"] = {"value": e2e_ms, "unit": "ms", "h2d_bytes": total * H4.FIELD.felt_bytes,
+            H4.merkle_root(hl[: 4 ** 6])     # warm the stream path
+            e2e_runs = []
+            for _ in range(2):               # the first run also grows the library's memory pool to 3 GiB; the second reuses it
+                t0 = time.perf_counter()
+                r_host = H4.merkle_root(hl)
+                e2e_runs.append((time.perf_counter() - t0) * 1e3)
+            e2e_ms = min(e2e_runs)
+            line["merkle"]["e2e"] = {"value": e2e_ms, "unit": "ms", "runs_ms": e2e_runs, "h2d_bytes": total * H4.FIELD.felt_bytes,
                                      "d2h_bytes": H4.FIELD.felt_bytes, "api": "anemoi_b200_merkle_root (host pointers, pinned)",
                                      "matches_device_path": "".join("%016x" % int(v) for v in reversed(r_host.reshape(-1).tolist())) == line["merkle"]["root"]}
             del host_leaves, hl
