@@ -35,6 +35,25 @@ def test_single_process_multi_gpu_root():
 
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
+def test_single_process_multi_gpu_root_with_chunked_upload():
+    """Slices big enough (>= 2^20 level-1 nodes per GPU) that every device uploads its slice in chunks and hashes the first
+    level while the next chunk is in flight, then joins the all-gather from its level-1 array: same root as the
+    device-resident single-GPU build (Pallas 4-3: 2 partial roots per rank; BLS12-377 2-1: 1 per rank)."""
+    import torch
+
+    from anemoi_rust_b200 import merkle
+
+    for H, h in ((A.AnemoiPallas_4_3, 12), (A.AnemoiBls12_377_2_1, 22)):
+        f, ar = H.FIELD, H.STATE_WIDTH
+        leaves = f.random_mont(ar ** h, 12)
+        dev = merkle.merkle_root_device(H, torch.from_numpy(leaves.view(np.int64)).cuda())
+        torch.cuda.synchronize()
+        exp = dev.cpu().numpy().view(np.uint64)
+        del dev
+        assert np.array_equal(H.merkle_root(leaves, 2), exp)
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
 def test_single_process_multi_gpu_compress():
     H = A.AnemoiBn254_4_3
     f = H.FIELD
