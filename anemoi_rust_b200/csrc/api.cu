@@ -189,6 +189,17 @@ struct DeviceScope {
     }
 };
 
+// `waiter` does not run past this point before everything enqueued on `producer` so far has finished.
+cudaError_t wait_for(cudaStream_t waiter, cudaStream_t producer) {
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(ev, producer);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(waiter, ev, 0);
+    cudaEventDestroy(ev);  // released by the runtime once the recorded work completes
+    return e;
+}
+
 // Generic host wrapper: copy `in_bytes` up, run `body(d_in, d_out, stream)`, copy `out_bytes` back.
 template <class Body>
 int host_call(int device, const void* in, size_t in_bytes, void* out, size_t out_bytes, bool in_place, Body body) {
@@ -250,20 +261,11 @@ int host_call_chunked(int device, const void* in, size_t in_unit, void* out, siz
             uint8_t* di = static_cast<uint8_t*>(d_in.p) + lo * in_unit;
             uint8_t* dout = static_cast<uint8_t*>(d_out.p) + lo * out_unit;
             cudaStream_t sc = s_cmp[c & 1];
-            cudaEvent_t up = nullptr, done = nullptr;
             if (fail(cudaMemcpyAsync(di, h_in + lo * in_unit, (hi - lo) * in_unit, cudaMemcpyHostToDevice, s_in), "H2D copy")) break;
-            if (fail(cudaEventCreateWithFlags(&up, cudaEventDisableTiming), "cudaEventCreate")) break;
-            fail(cudaEventRecord(up, s_in), "cudaEventRecord");
-            fail(cudaStreamWaitEvent(sc, up, 0), "cudaStreamWaitEvent");
-            cudaEventDestroy(up);
-            if (rc) break;
+            if (fail(wait_for(sc, s_in), "stream ordering")) break;
             rc = body(di, dout, hi - lo, sc);
             if (rc) break;
-            if (fail(cudaEventCreateWithFlags(&done, cudaEventDisableTiming), "cudaEventCreate")) break;
-            fail(cudaEventRecord(done, sc), "cudaEventRecord");
-            fail(cudaStreamWaitEvent(s_out, done, 0), "cudaStreamWaitEvent");
-            cudaEventDestroy(done);
-            if (rc) break;
+            if (fail(wait_for(s_out, sc), "stream ordering")) break;
             fail(cudaMemcpyAsync(h_out + lo * out_unit, dout, (hi - lo) * out_unit, cudaMemcpyDeviceToHost, s_out), "D2H copy");
         }
         // everything must have finished before the buffers are released (and before the caller reads `out`)
@@ -320,6 +322,24 @@ int anemoi_b200_pool_trim(int device, size_t keep_bytes) {
     CK(cudaDeviceSynchronize());
     CK(cudaMemPoolTrimTo(pool, keep_bytes));
     return ANEMOI_B200_OK;
+}
+
+int anemoi_b200_pool_reserve(int device, size_t bytes) {
+    DeviceScope scope(device);
+    if (scope.rc != ANEMOI_B200_OK) return scope.rc;
+    if (bytes == 0) return ANEMOI_B200_OK;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = ANEMOI_B200_OK;
+    {
+        DevBuf block;  // one allocation of the whole size, handed straight back: the pool keeps the memory
+        cudaError_t e = block.alloc_async(bytes, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "device allocation");
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamDestroy(st);
+    return rc;
 }
 
 int anemoi_b200_device_count(void) {
@@ -1023,22 +1043,14 @@ int anemoi_b200_merkle_root(int field, int inst, int arity, const uint64_t* leav
                         return ANEMOI_B200_OK;
                     }
                     CK(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
-                    cudaEvent_t ready;
-                    CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-                    CK(cudaEventRecord(ready, d.st));           // the buffers exist (stream-ordered allocation) ...
-                    CK(cudaStreamWaitEvent(d.copy, ready, 0));  // ... before the copy stream writes into them
-                    CK(cudaEventDestroy(ready));
+                    CK(wait_for(d.copy, d.st));  // the buffers exist (stream-ordered allocation) before the copy stream writes into them
                     const size_t nodes_per_chunk = level1_nodes / (size_t)chunks, leaves_per_chunk = nodes_per_chunk * (size_t)arity;
                     const int mode = arity == 2 ? anemoi::MODE_COMPRESS : anemoi::MODE_COMPRESS4;
                     for (int c = 0; c < chunks; c++) {
                         uint64_t* d_chunk = (uint64_t*)d.leaves.p + (size_t)c * leaves_per_chunk * words;
                         CK(cudaMemcpyAsync(d_chunk, src + (size_t)c * leaves_per_chunk * words, leaves_per_chunk * fb,
                                            cudaMemcpyHostToDevice, d.copy));
-                        cudaEvent_t arrived;
-                        CK(cudaEventCreateWithFlags(&arrived, cudaEventDisableTiming));
-                        CK(cudaEventRecord(arrived, d.copy));
-                        CK(cudaStreamWaitEvent(d.st, arrived, 0));
-                        CK(cudaEventDestroy(arrived));
+                        CK(wait_for(d.st, d.copy));
                         int r1 = launch(field, inst, mode, d_chunk, (uint64_t*)d.level1.p + (size_t)c * nodes_per_chunk * words, nullptr,
                                         nodes_per_chunk, 0, d.st);
                         if (r1) return r1;

@@ -80,6 +80,7 @@ _SIGS = {
     "anemoi_b200_comm_info": ([_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)], _i),
     "anemoi_b200_comm_destroy": ([_vp], _i),
     "anemoi_b200_pool_trim": ([_i, _sz], _i),
+    "anemoi_b200_pool_reserve": ([_i, _sz], _i),
     "anemoi_b200_count_noncanonical": ([_i, _vp, _sz, _vp, _i], _i),
     "anemoi_b200_count_noncanonical_dev": ([_i, _vp, _sz, _vp, _vp], _i),
     "anemoi_b200_merkle_tree_felts": ([_i, _sz], _sz),

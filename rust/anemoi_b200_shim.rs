@@ -38,6 +38,7 @@ extern "C" {
     pub fn anemoi_b200_num_rounds(field: c_int, inst: c_int) -> c_int;
     pub fn anemoi_b200_field_name(field: c_int) -> *const c_char;
     pub fn anemoi_b200_pool_trim(device: c_int, keep_bytes: usize) -> c_int;
+    pub fn anemoi_b200_pool_reserve(device: c_int, bytes: usize) -> c_int;
     pub fn anemoi_b200_permute(field: c_int, inst: c_int, states: *mut u64, n: usize, device: c_int) -> c_int;
     pub fn anemoi_b200_sbox_layer(field: c_int, inst: c_int, states: *mut u64, n: usize, device: c_int) -> c_int;
     pub fn anemoi_b200_layer(field: c_int, inst: c_int, layer: c_int, round: c_int, states: *mut u64, n: usize, device: c_int) -> c_int;

@@ -301,3 +301,8 @@ def test_latency_and_throughput_forms_agree(field, inst):
         assert np.array_equal(o, outs[-1][:n]), "n = %d differs from the largest batch" % n
     ffi.check(ffi.lib.anemoi_b200_pool_trim(0, 0))   # hand the cached device buffers back; the next call re-allocates
     assert np.array_equal(H.compress_k_batch(x[: 100 * W], W), ref)
+    ffi.check(ffi.lib.anemoi_b200_pool_trim(0, 0))
+    ffi.check(ffi.lib.anemoi_b200_pool_reserve(0, 64 << 20))   # grow the pool ahead of the call instead
+    assert np.array_equal(H.compress_k_batch(x[: 100 * W], W), ref)
+    assert ffi.lib.anemoi_b200_pool_reserve(0, 0) == 0
+    assert ffi.lib.anemoi_b200_pool_reserve(1 << 20, 16) == ffi.ERR_ARG   # no such device
