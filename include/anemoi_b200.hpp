@@ -40,6 +40,10 @@ inline void check(int rc) {
     throw Error(rc);
 }
 
+// The library's device-memory pool (buffers of the host-pointer calls): grow it ahead of the first big call / hand it back.
+inline void pool_reserve(int device, size_t bytes) { check(anemoi_b200_pool_reserve(device, bytes)); }
+inline void pool_trim(int device, size_t keep_bytes = 0) { check(anemoi_b200_pool_trim(device, keep_bytes)); }
+
 // NCCL communicator owned by the library (anemoi_b200_comm_*): rank 0 draws the 128-byte id, the host ships it to the
 // other ranks by its own transport, every rank joins with its CUDA device current. Used by merkle_root_sharded_dev.
 struct Comm {

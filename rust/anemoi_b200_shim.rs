@@ -293,6 +293,16 @@ pub trait B200Batch<F: PrimeField> {
     }
 }
 
+/// Grows the library's device-memory pool (buffers of the host-pointer calls) ahead of the first big call.
+pub fn pool_reserve(device: usize, bytes: usize) {
+    check(unsafe { anemoi_b200_pool_reserve(device as c_int, bytes) });
+}
+
+/// Hands the pool's cached device memory back to the driver, keeping at most `keep_bytes`.
+pub fn pool_trim(device: usize, keep_bytes: usize) {
+    check(unsafe { anemoi_b200_pool_trim(device as c_int, keep_bytes) });
+}
+
 /// Device-resident, stream-ordered forms: raw device pointers to `[F]` / `[u64; N]` limb arrays on the CURRENT CUDA
 /// device and a `cudaStream_t` (as `*mut c_void`; null = legacy default stream). They only enqueue work.
 pub mod dev {
