@@ -14,3 +14,13 @@ __version__ = "0.1.0"
 
 def device_count():
     return ffi.lib.anemoi_b200_device_count()
+
+
+def pool_reserve(device, nbytes):
+    """Grow the library's device-memory pool (buffers of the host-pointer calls) ahead of the first big call."""
+    ffi.check(ffi.lib.anemoi_b200_pool_reserve(int(device), int(nbytes)))
+
+
+def pool_trim(device, keep_bytes=0):
+    """Hand the pool's cached device memory back to the driver, keeping at most keep_bytes."""
+    ffi.check(ffi.lib.anemoi_b200_pool_trim(int(device), int(keep_bytes)))
