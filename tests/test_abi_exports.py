@@ -72,6 +72,11 @@ def test_argument_errors_without_a_device():
 
         with pytest.raises(A.NoDeviceError):
             A.AnemoiBls12_381_2_1.compress([0, 1])
+        # the operational entries too: nothing pretends to have reserved device memory
+        assert lib.anemoi_b200_pool_reserve(0, 1 << 20) == ffi.ERR_NO_DEVICE
+        assert lib.anemoi_b200_pool_trim(0, 0) == ffi.ERR_NO_DEVICE
+        with pytest.raises(A.NoDeviceError):
+            A.pool_reserve(0, 1 << 20)
 
 
 def test_sharded_plan_in_c_matches_python_plan():
